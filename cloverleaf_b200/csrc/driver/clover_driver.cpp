@@ -90,6 +90,7 @@ struct Backend {
   void (*x_min)(dp) = nullptr;
   void (*x_sum)(dp, ip) = nullptr;
   void (*x_sync_to_host)(ip) = nullptr;
+  void (*x_forget)(dp) = nullptr;
 };
 
 template <class F>
@@ -263,6 +264,7 @@ bool clover_driver::load_backend(const char* path) {
   sym(h, "clover_b200_min_", be.x_min, false, ignore);
   sym(h, "clover_b200_sum_", be.x_sum, false, ignore);
   sym(h, "clover_b200_sync_to_host_", be.x_sync_to_host, false, ignore);
+  sym(h, "clover_b200_forget_", be.x_forget, false, ignore);
   if (!e.empty()) {
     error = "backend " + std::string(path) + ":" + e;
     return false;
@@ -892,6 +894,10 @@ void clover_driver_sync_to_host(clover_driver* d) {
 
 void clover_driver_destroy(clover_driver* d) {
   if (!d) return;
+  // a GPU backend keys its device mirrors by host address: drop them before the addresses are recycled
+  if (d->be.x_forget)
+    for (Chunk& c : d->chunks)
+      for (void* p : c.allocs) d->be.x_forget((dp)p);
   for (Chunk& c : d->chunks) c.release();
   if (d->out) fclose(d->out);
   // the backend handle is intentionally left open (device state lives in it)

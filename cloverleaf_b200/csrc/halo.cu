@@ -1,0 +1,541 @@
+// halo.cu -- reflective boundary (update_halo), halo message pack/unpack, the NCCL halo exchange and
+// scalar reductions that replace clover_exchange / clover_min / clover_sum, and the two set-up
+// kernels (initialise_chunk, generate_chunk).  fp64 CUDA for sm_100a.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+
+#include "clover_b200.h"
+#include "common.cuh"
+
+namespace clv {
+
+// from runtime.cu
+bool chunk_registered();
+int chunk_nx();
+int chunk_ny();
+const int* chunk_neighbours();
+double* chunk_field_host(int f);
+void count_copy(long long h2d, long long d2h);
+
+// Field geometry by id (data.f90:51-66; types as in clover.f90:690-880 / update_halo_kernel_c.c):
+// x_inc,y_inc = extra vertices; m = 0 for cell-centred data, 1 otherwise; sx,sy = sign applied when
+// reflecting about a left/right resp. bottom/top wall.
+struct FieldDesc {
+  double* p;
+  int x_inc, y_inc, m;
+  double sx, sy;
+  int offset;  // message offset in doubles (exchange only)
+};
+struct FieldTable {
+  FieldDesc f[15];
+  int n;
+};
+static const struct { int x_inc, y_inc, m; double sx, sy; Kind kind; } kFieldGeom[15] = {
+    {0, 0, 0, 1.0, 1.0, CELL},     // density0
+    {0, 0, 0, 1.0, 1.0, CELL},     // density1
+    {0, 0, 0, 1.0, 1.0, CELL},     // energy0
+    {0, 0, 0, 1.0, 1.0, CELL},     // energy1
+    {0, 0, 0, 1.0, 1.0, CELL},     // pressure
+    {0, 0, 0, 1.0, 1.0, CELL},     // viscosity
+    {0, 0, 0, 1.0, 1.0, CELL},     // soundspeed
+    {1, 1, 1, -1.0, 1.0, VERTEX},  // xvel0
+    {1, 1, 1, -1.0, 1.0, VERTEX},  // xvel1
+    {1, 1, 1, 1.0, -1.0, VERTEX},  // yvel0
+    {1, 1, 1, 1.0, -1.0, VERTEX},  // yvel1
+    {1, 0, 1, -1.0, 1.0, XFACE},   // vol_flux_x
+    {0, 1, 1, 1.0, -1.0, YFACE},   // vol_flux_y
+    {1, 0, 1, -1.0, 1.0, XFACE},   // mass_flux_x
+    {0, 1, 1, 1.0, -1.0, YFACE},   // mass_flux_y
+};
+
+// ------------------------------------------------------------------------------------------------
+// update_halo_kernel_c.c:86-712 as ONE pass.  The reference does, per field, bottom, top, then left,
+// right (the latter over the already reflected halo rows, which is what fills the corners).  Every
+// destination cell of that sequence is a pure function of never-written cells:
+//     f(jd,kd) = [sx if jd reflected] * [sy if kd reflected] * f(js,ks)
+// with js/ks the mirror index when (jd resp. kd) lies beyond an EXTERNAL face, else the index itself
+// (halo data received from a neighbour chunk).  Mirror rules:
+//     bottom: 1-k <- m+k         top:   ny+y_inc+k <- ny+y_inc+(1-m)-k
+//     left:   1-j <- m+j         right: nx+x_inc+j <- nx+x_inc+(1-m)-j
+__global__ void __launch_bounds__(256)
+    update_halo_kernel(FieldTable T, int nx, int ny, int pitch, int depth, int ext_left, int ext_right,
+                       int ext_bottom, int ext_top) {
+  const FieldDesc F = T.f[blockIdx.y];
+  const int W = nx + F.x_inc + 2 * depth;  // width of the bottom/top strips (corners included)
+  const int H = ny + F.y_inc;              // height of the left/right strips (corners excluded)
+  const int n_bt = 2 * depth * W, n_lr = 2 * depth * H;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_bt + n_lr) return;
+  int jd, kd;
+  if (t < n_bt) {
+    const int side = t / (depth * W), r = (t % (depth * W)) / W + 1;
+    jd = 1 - depth + (t % W);
+    kd = side == 0 ? 1 - r : ny + F.y_inc + r;
+  } else {
+    const int u = t - n_bt;
+    const int side = u / (depth * H), r = (u % (depth * H)) / H + 1;
+    kd = 1 + (u % H);
+    jd = side == 0 ? 1 - r : nx + F.x_inc + r;
+  }
+  const bool refl_x = (jd < 1 && ext_left) || (jd > nx + F.x_inc && ext_right);
+  const bool refl_y = (kd < 1 && ext_bottom) || (kd > ny + F.y_inc && ext_top);
+  if (!refl_x && !refl_y) return;
+  int js = jd, ks = kd;
+  double sign = 1.0;
+  if (refl_x) {
+    js = (jd < 1) ? F.m + (1 - jd) : nx + F.x_inc + (1 - F.m) - (jd - (nx + F.x_inc));
+    sign = sign * F.sx;
+  }
+  if (refl_y) {
+    ks = (kd < 1) ? F.m + (1 - kd) : ny + F.y_inc + (1 - F.m) - (kd - (ny + F.y_inc));
+    sign = sign * F.sy;
+  }
+  F.p[idx2(pitch, jd, kd)] = sign * F.p[idx2(pitch, js, ks)];
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack_kernel_c.c:29-439, all fields of one face in one launch.  face: 0 left, 1 right, 2 bottom, 3 top.
+// Message index (0-based): left/right  off + (jj-1) + (k+depth-1)*depth,  k = 1-depth .. ny+y_inc+depth
+//                          bottom/top  off + (kk-1) + (j+depth-1)*depth,  j = 1-depth .. nx+x_inc+depth
+template <bool UNPACK>
+__global__ void __launch_bounds__(256)
+    halo_message_kernel(FieldTable T, int nx, int ny, int pitch, int depth, int face, double* __restrict__ buffer) {
+  const FieldDesc F = T.f[blockIdx.y];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int j, k, index;
+  if (face < 2) {
+    const int span = ny + F.y_inc + 2 * depth;
+    if (t >= span * depth) return;
+    const int jj = t % depth + 1, kk = t / depth;  // kk = k + depth - 1
+    k = kk - depth + 1;
+    index = F.offset + (jj - 1) + kk * depth;
+    if (face == 0) j = UNPACK ? 1 - jj : 1 + F.x_inc - 1 + jj;
+    else           j = UNPACK ? nx + F.x_inc + jj : nx + 1 - jj;
+  } else {
+    const int span = nx + F.x_inc + 2 * depth;
+    if (t >= span * depth) return;
+    // consecutive threads walk along j (unit stride in the field); message stride is `depth`
+    const int kk = t / span + 1, jx = t % span;  // jx = j + depth - 1
+    j = jx - depth + 1;
+    index = F.offset + (kk - 1) + jx * depth;
+    if (face == 2) k = UNPACK ? 1 - kk : 1 + F.y_inc - 1 + kk;
+    else           k = UNPACK ? ny + F.y_inc + kk : ny + 1 - kk;
+  }
+  if (UNPACK) F.p[idx2(pitch, j, k)] = buffer[index];
+  else        buffer[index] = F.p[idx2(pitch, j, k)];
+}
+
+static void launch_message(bool unpack, const FieldTable& T, const Grid& g, int depth, int face, double* buffer) {
+  const int edge = (face < 2 ? g.ny : g.nx) + 1 + 2 * depth;
+  const dim3 grid((unsigned)((edge * depth + 255) / 256), (unsigned)T.n);
+  LaunchScope ls(unpack ? "halo_unpack" : "halo_pack");
+  if (unpack) halo_message_kernel<true><<<grid, 256, 0, stream()>>>(T, g.nx, g.ny, g.pitch, depth, face, buffer);
+  else        halo_message_kernel<false><<<grid, 256, 0, stream()>>>(T, g.nx, g.ny, g.pitch, depth, face, buffer);
+}
+
+// ABI pack/unpack of one field: the message buffer is a HOST array handed to MPI by the caller, so
+// the packed strip is copied back (pack) or in (unpack) right here, in both residency modes.
+static void abi_message(int face, bool unpack, int* xmin, int* xmax, int* ymin, int* ymax, double* field,
+                        double* buffer, int* cell, int* vertex, int* xface, int* yface, int* depth_p,
+                        int* field_type, int* buffer_offset) {
+  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+  const int depth = *depth_p, type = *field_type;
+  FieldTable T;
+  T.n = 1;
+  FieldDesc& F = T.f[0];
+  Kind kind;
+  if (type == *cell) { F.x_inc = 0; F.y_inc = 0; kind = CELL; }
+  else if (type == *vertex) { F.x_inc = 1; F.y_inc = 1; kind = VERTEX; }
+  else if (type == *xface) { F.x_inc = 1; F.y_inc = 0; kind = XFACE; }
+  else if (type == *yface) { F.x_inc = 0; F.y_inc = 1; kind = YFACE; }
+  else fatal("pack/unpack: unknown field_type %d", type);
+  F.m = 0; F.sx = F.sy = 1.0;
+  F.offset = *buffer_offset;
+  const size_t lo = (size_t)F.offset;
+  const size_t span = (size_t)((face < 2 ? g.ny + F.y_inc : g.nx + F.x_inc) + 2 * depth);
+  const size_t hi = lo + span * depth;
+  F.p = dev(g, field, kind, unpack ? INOUT : IN);
+  double* dbuf = dev_buffer(buffer, hi, unpack ? IN : 0, lo, hi);
+  launch_message(unpack, T, g, depth, face, dbuf);
+  if (!unpack) {
+    CLV_CUDA(cudaMemcpyAsync(buffer + lo, dbuf + lo, (hi - lo) * sizeof(double), cudaMemcpyDeviceToHost, stream()));
+    count_copy(0, (long long)((hi - lo) * sizeof(double)));
+    CLV_CUDA(cudaStreamSynchronize(stream()));
+  }
+  finish();
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL (loaded lazily so that single-GPU runs never need it and so that a process that already
+// holds torch's libnccl shares that copy)
+struct Nccl {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+  double* snd[4] = {};
+  double* rcv[4] = {};
+  size_t cap[4] = {};
+  double* d_scal = nullptr;
+} N;
+
+#define CLV_NCCL(call)                                                                          \
+  do {                                                                                          \
+    ncclResult_t r_ = (call);                                                                   \
+    if (r_ != ncclSuccess) fatal("NCCL error at %s:%d: %s", __FILE__, __LINE__, N.GetErrorString(r_)); \
+  } while (0)
+
+static void nccl_load() {
+  if (N.lib) return;
+  N.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!N.lib) N.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!N.lib) N.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!N.lib) fatal("cannot load libnccl.so.2: %s", dlerror());
+#define LOAD(field, name)                                        \
+  *(void**)(&N.field) = dlsym(N.lib, name);                      \
+  if (!N.field) fatal("libnccl lacks %s", name)
+  LOAD(GetUniqueId, "ncclGetUniqueId");
+  LOAD(CommInitRank, "ncclCommInitRank");
+  LOAD(CommDestroy, "ncclCommDestroy");
+  LOAD(Send, "ncclSend");
+  LOAD(Recv, "ncclRecv");
+  LOAD(GroupStart, "ncclGroupStart");
+  LOAD(GroupEnd, "ncclGroupEnd");
+  LOAD(AllReduce, "ncclAllReduce");
+  LOAD(GetErrorString, "ncclGetErrorString");
+#undef LOAD
+}
+
+static void ensure_msg_buffers(int face, size_t doubles) {
+  if (N.cap[face] >= doubles) return;
+  CLV_CUDA(cudaStreamSynchronize(stream()));
+  if (N.snd[face]) CLV_CUDA(cudaFree(N.snd[face]));
+  if (N.rcv[face]) CLV_CUDA(cudaFree(N.rcv[face]));
+  CLV_CUDA(cudaMalloc(&N.snd[face], doubles * sizeof(double)));
+  CLV_CUDA(cudaMalloc(&N.rcv[face], doubles * sizeof(double)));
+  N.cap[face] = doubles;
+}
+
+// ------------------------------------------------------------------------------------------------
+// initialise_chunk_kernel_c.c:60-121
+__global__ void init_chunk_1d_kernel(int nx, int ny, double min_x, double min_y, double d_x, double d_y,
+                                     double* vertexx, double* vertexdx, double* vertexy, double* vertexdy,
+                                     double* cellx, double* celldx, double* celly, double* celldy) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;  // t = index - lower bound(-1)
+  const int j = t - 1;                                   // Fortran index; x_min = y_min = 1
+  if (t <= nx + 4) {
+    vertexx[t] = min_x + d_x * (double)(j - 1);
+    vertexdx[t] = d_x;
+  }
+  if (t <= nx + 3) {
+    cellx[t] = 0.5 * ((min_x + d_x * (double)(j - 1)) + (min_x + d_x * (double)(j + 1 - 1)));
+    celldx[t] = d_x;
+  }
+  if (t <= ny + 4) {
+    vertexy[t] = min_y + d_y * (double)(j - 1);
+    vertexdy[t] = d_y;
+  }
+  if (t <= ny + 3) {
+    celly[t] = 0.5 * ((min_y + d_y * (double)(j - 1)) + (min_y + d_y * (double)(j + 1 - 1)));
+    celldy[t] = d_y;
+  }
+}
+__global__ void init_chunk_2d_kernel(int nx, int ny, int pitch, double d_x, double d_y, double* volume,
+                                     double* xarea, double* yarea) {
+  const int j = -XOFF + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int k = -1 + (int)(blockIdx.y * blockDim.y + threadIdx.y);
+  if (j < -1 || j > nx + 2 || k > ny + 2) return;
+  const size_t c = idx2(pitch, j, k);
+  volume[c] = d_x * d_y;
+  xarea[c] = d_y;  // celldy(k)
+  yarea[c] = d_x;  // celldx(j)
+}
+
+// generate_chunk_kernel_c.c:70-158, gathered per destination instead of scattered per cell: a cell
+// takes the LAST state (2..n) whose geometry test it passes; a vertex takes the velocity of the last
+// state that any of its (up to four) adjacent cells passes.
+constexpr int MAX_STATES = 24;
+struct States {
+  int n;
+  int geometry[MAX_STATES];
+  double density[MAX_STATES], energy[MAX_STATES], xvel[MAX_STATES], yvel[MAX_STATES];
+  double xmin[MAX_STATES], xmax[MAX_STATES], ymin[MAX_STATES], ymax[MAX_STATES], radius[MAX_STATES];
+  int g_rect, g_circ, g_point;
+};
+__device__ __forceinline__ bool state_hits(const States& S, int s, int j, int k, int ny_len, const double* vertexx,
+                                           const double* vertexy, const double* cellx, const double* celly) {
+  if (S.geometry[s] == S.g_rect)
+    return vertexx[j + 2] >= S.xmin[s] && vertexx[j + 1] < S.xmax[s] && vertexy[k + 2] >= S.ymin[s] &&
+           vertexy[k + 1] < S.ymax[s];
+  if (S.geometry[s] == S.g_circ) {
+    const double x_cent = S.xmin[s], y_cent = S.ymin[s];
+    const double radius = sqrt((cellx[j + 1] - x_cent) * (cellx[j + 1] - x_cent) +
+                               (celly[k + 1] - y_cent) * (celly[k + 1] - y_cent));
+    return radius <= S.radius[s];
+  }
+  if (S.geometry[s] == S.g_point)  // :143 reads vertexy at index j
+    return vertexx[j + 1] == S.xmin[s] && vertexy[(j + 1 < ny_len) ? j + 1 : ny_len - 1] == S.ymin[s];
+  return false;
+}
+__global__ void generate_chunk_kernel(States S, int nx, int ny, int pitch, const double* __restrict__ vertexx,
+                                      const double* __restrict__ vertexy, const double* __restrict__ cellx,
+                                      const double* __restrict__ celly, double* __restrict__ density0,
+                                      double* __restrict__ energy0, double* __restrict__ xvel0,
+                                      double* __restrict__ yvel0) {
+  const int j = -XOFF + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int k = -1 + (int)(blockIdx.y * blockDim.y + threadIdx.y);
+  if (j < -1 || j > nx + 3 || k > ny + 3) return;
+  const size_t c = idx2(pitch, j, k);
+  if (j <= nx + 2 && k <= ny + 2) {
+    double rho = S.density[0], e = S.energy[0];
+    for (int s = 1; s < S.n; ++s)
+      if (state_hits(S, s, j, k, ny + 5, vertexx, vertexy, cellx, celly)) {
+        rho = S.density[s];
+        e = (S.geometry[s] == S.g_rect) ? S.energy[s] : S.density[s];  // :134,:145 quirk
+      }
+    density0[c] = rho;
+    energy0[c] = e;
+  }
+  bool set = (j <= nx + 2 && k <= ny + 2);
+  double u = S.xvel[0], v = S.yvel[0];
+  for (int s = 1; s < S.n; ++s) {
+    bool hit = false;
+    for (int ck = k - 1; ck <= k; ++ck)
+      for (int cj = j - 1; cj <= j; ++cj)
+        if (cj >= -1 && cj <= nx + 2 && ck >= -1 && ck <= ny + 2)
+          hit = hit || state_hits(S, s, cj, ck, ny + 5, vertexx, vertexy, cellx, celly);
+    if (hit) { u = S.xvel[s]; v = S.yvel[s]; set = true; }
+  }
+  if (set) { xvel0[c] = u; yvel0[c] = v; }
+}
+
+}  // namespace clv
+
+using namespace clv;
+
+extern "C" {
+
+void update_halo_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, int* chunk_neighbours,
+                           int* tile_neighbours, double* density0, double* energy0, double* pressure,
+                           double* viscosity, double* soundspeed, double* density1, double* energy1,
+                           double* xvel0, double* yvel0, double* xvel1, double* yvel1, double* vol_flux_x,
+                           double* vol_flux_y, double* mass_flux_x, double* mass_flux_y, int* fields,
+                           int* depth_p) {
+  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+  const int depth = *depth_p;
+  if (depth < 1 || depth > 2) fatal("update_halo: depth %d", depth);
+  int ext[4];
+  for (int f = 0; f < 4; ++f) ext[f] = (chunk_neighbours[f] == -1 && tile_neighbours[f] == -1);
+  double* host[15] = {density0, density1, energy0, energy1, pressure, viscosity, soundspeed, xvel0,
+                      xvel1, yvel0, yvel1, vol_flux_x, vol_flux_y, mass_flux_x, mass_flux_y};
+  FieldTable T;
+  T.n = 0;
+  for (int f = 0; f < 15; ++f) {
+    if (fields[f] != 1) continue;
+    FieldDesc& F = T.f[T.n++];
+    F.p = dev(g, host[f], kFieldGeom[f].kind, INOUT);
+    F.x_inc = kFieldGeom[f].x_inc; F.y_inc = kFieldGeom[f].y_inc; F.m = kFieldGeom[f].m;
+    F.sx = kFieldGeom[f].sx; F.sy = kFieldGeom[f].sy; F.offset = 0;
+  }
+  if (T.n > 0 && (ext[0] || ext[1] || ext[2] || ext[3])) {
+    const int ring = 2 * depth * (g.nx + 1 + 2 * depth) + 2 * depth * (g.ny + 1);
+    const dim3 grid((unsigned)((ring + 255) / 256), (unsigned)T.n);
+    LaunchScope ls("update_halo");
+    update_halo_kernel<<<grid, 256, 0, stream()>>>(T, g.nx, g.ny, g.pitch, depth, ext[0], ext[1], ext[2], ext[3]);
+  }
+  finish();
+}
+
+#define CLV_PACK_ENTRY(name, face, unpack)                                                          \
+  void name(int* xmin, int* xmax, int* ymin, int* ymax, double* field, double* buffer, int* c, int* v, \
+            int* xf, int* yf, int* depth, int* field_type, int* buffer_offset) {                     \
+    abi_message(face, unpack, xmin, xmax, ymin, ymax, field, buffer, c, v, xf, yf, depth, field_type, \
+                buffer_offset);                                                                      \
+  }
+CLV_PACK_ENTRY(clover_pack_message_left_c_, 0, false)
+CLV_PACK_ENTRY(clover_unpack_message_left_c_, 0, true)
+CLV_PACK_ENTRY(clover_pack_message_right_c_, 1, false)
+CLV_PACK_ENTRY(clover_unpack_message_right_c_, 1, true)
+CLV_PACK_ENTRY(clover_pack_message_bottom_c_, 2, false)
+CLV_PACK_ENTRY(clover_unpack_message_bottom_c_, 2, true)
+CLV_PACK_ENTRY(clover_pack_message_top_c_, 3, false)
+CLV_PACK_ENTRY(clover_unpack_message_top_c_, 3, true)
+
+// ---- communicator + exchange ---------------------------------------------------------------------
+void clover_b200_comm_get_unique_id_(char* id128) {
+  ensure_init();
+  nccl_load();
+  ncclUniqueId id;
+  CLV_NCCL(N.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128, &id, 128);
+}
+
+void clover_b200_comm_init_(int* nranks, int* rank, char* id128) {
+  ensure_init();
+  nccl_load();
+  if (N.comm) fatal("comm_init called twice");
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  N.nranks = *nranks;
+  N.rank = *rank;
+  CLV_NCCL(N.CommInitRank(&N.comm, N.nranks, id, N.rank));
+  CLV_CUDA(cudaMalloc(&N.d_scal, 16 * sizeof(double)));
+}
+
+void clover_b200_comm_finalize_internal() {
+  if (N.comm) {
+    N.CommDestroy(N.comm);
+    N.comm = nullptr;
+  }
+  for (int f = 0; f < 4; ++f) {
+    if (N.snd[f]) cudaFree(N.snd[f]);
+    if (N.rcv[f]) cudaFree(N.rcv[f]);
+    N.snd[f] = N.rcv[f] = nullptr;
+    N.cap[f] = 0;
+  }
+  if (N.d_scal) cudaFree(N.d_scal);
+  N.d_scal = nullptr;
+  N.nranks = 1;
+  N.rank = 0;
+}
+
+void clover_b200_exchange_(int* fields, int* depth_p) {
+  ensure_init();
+  if (!chunk_registered()) fatal("exchange before register_chunk");
+  const int* nb = chunk_neighbours();
+  if (nb[0] == -1 && nb[1] == -1 && nb[2] == -1 && nb[3] == -1) return;
+  if (!N.comm) fatal("exchange with neighbours but no communicator (call clover_b200_comm_init_)");
+  const int depth = *depth_p;
+  int one = 1, nx = chunk_nx(), ny = chunk_ny();
+  const Grid g = grid_of(&one, &nx, &one, &ny);
+  // clover.f90:368-375: per-field offsets are running sums of depth*(edge+5)
+  for (int phase = 0; phase < 2; ++phase) {
+    const int fa = phase * 2, fb = fa + 1;
+    if (nb[fa] == -1 && nb[fb] == -1) continue;
+    const int edge = (phase == 0 ? g.ny : g.nx) + 5;
+    FieldTable T;
+    T.n = 0;
+    int off = 0;
+    for (int f = 0; f < 15; ++f) {
+      if (fields[f] != 1) continue;
+      FieldDesc& F = T.f[T.n++];
+      F.p = dev(g, chunk_field_host(f), kFieldGeom[f].kind, INOUT);
+      F.x_inc = kFieldGeom[f].x_inc; F.y_inc = kFieldGeom[f].y_inc; F.m = kFieldGeom[f].m;
+      F.sx = kFieldGeom[f].sx; F.sy = kFieldGeom[f].sy;
+      F.offset = off;
+      off += depth * edge;
+    }
+    if (T.n == 0) return;
+    const size_t total = (size_t)off;
+    for (int face = fa; face <= fb; ++face) {
+      if (nb[face] == -1) continue;
+      ensure_msg_buffers(face, (size_t)15 * 2 * edge);
+      launch_message(false, T, g, depth, face, N.snd[face]);
+    }
+    CLV_NCCL(N.GroupStart());
+    for (int face = fa; face <= fb; ++face) {
+      if (nb[face] == -1) continue;
+      const int peer = nb[face] - 1;  // rank = chunk - 1 (clover.f90:892)
+      CLV_NCCL(N.Send(N.snd[face], total, ncclDouble, peer, N.comm, stream()));
+      CLV_NCCL(N.Recv(N.rcv[face], total, ncclDouble, peer, N.comm, stream()));
+    }
+    CLV_NCCL(N.GroupEnd());
+    for (int face = fa; face <= fb; ++face) {
+      if (nb[face] == -1) continue;
+      launch_message(true, T, g, depth, face, N.rcv[face]);
+    }
+  }
+  finish();
+}
+
+static void allreduce_host(double* values, int n, ncclRedOp_t op) {
+  ensure_init();
+  if (!N.comm || N.nranks == 1) return;
+  if (n > 16) fatal("allreduce of %d values (max 16)", n);
+  CLV_CUDA(cudaMemcpyAsync(N.d_scal, values, n * sizeof(double), cudaMemcpyHostToDevice, stream()));
+  CLV_NCCL(N.AllReduce(N.d_scal, N.d_scal, (size_t)n, ncclDouble, op, N.comm, stream()));
+  CLV_CUDA(cudaMemcpyAsync(values, N.d_scal, n * sizeof(double), cudaMemcpyDeviceToHost, stream()));
+  CLV_CUDA(cudaStreamSynchronize(stream()));
+}
+void clover_b200_min_(double* value) { allreduce_host(value, 1, ncclMin); }
+void clover_b200_sum_(double* values, int* n) { allreduce_host(values, *n, ncclSum); }
+
+// ---- set-up kernels -------------------------------------------------------------------------------
+void initialise_chunk_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* min_x, double* min_y,
+                                double* dx, double* dy, double* vertexx, double* vertexdx, double* vertexy,
+                                double* vertexdy, double* cellx, double* celldx, double* celly,
+                                double* celldy, double* volume, double* xarea, double* yarea) {
+  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+  double* vx = dev(g, vertexx, X1D_VERT, OUT);
+  double* vdx = dev(g, vertexdx, X1D_VERT, OUT);
+  double* vy = dev(g, vertexy, Y1D_VERT, OUT);
+  double* vdy = dev(g, vertexdy, Y1D_VERT, OUT);
+  double* cx = dev(g, cellx, X1D_CELL, OUT);
+  double* cdx = dev(g, celldx, X1D_CELL, OUT);
+  double* cy = dev(g, celly, Y1D_CELL, OUT);
+  double* cdy = dev(g, celldy, Y1D_CELL, OUT);
+  double* vol = dev(g, volume, CELL, OUT);
+  double* xa = dev(g, xarea, XFACE, OUT);
+  double* ya = dev(g, yarea, YFACE, OUT);
+  const int n1 = (g.nx > g.ny ? g.nx : g.ny) + 5;
+  {
+    LaunchScope ls("initialise_chunk_1d");
+    init_chunk_1d_kernel<<<(n1 + 255) / 256, 256, 0, stream()>>>(g.nx, g.ny, *min_x, *min_y, *dx, *dy, vx, vdx, vy,
+                                                                 vdy, cx, cdx, cy, cdy);
+  }
+  {
+    const dim3 block(32, 8), grid((unsigned)((g.nx + 3 + XOFF + 32) / 32), (unsigned)((g.ny + 4 + 7) / 8));
+    LaunchScope ls("initialise_chunk_2d");
+    init_chunk_2d_kernel<<<grid, block, 0, stream()>>>(g.nx, g.ny, g.pitch, *dx, *dy, vol, xa, ya);
+  }
+  finish();
+}
+
+void generate_chunk_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* vertexx, double* vertexy,
+                              double* cellx, double* celly, double* density0, double* energy0,
+                              double* xvel0, double* yvel0, int* number_of_states, double* state_density,
+                              double* state_energy, double* state_xvel, double* state_yvel,
+                              double* state_xmin, double* state_xmax, double* state_ymin,
+                              double* state_ymax, double* state_radius, int* state_geometry, int* g_rect,
+                              int* g_circ, int* g_point) {
+  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+  States S;
+  S.n = *number_of_states;
+  if (S.n < 1 || S.n > MAX_STATES) fatal("generate_chunk: %d states (max %d)", S.n, MAX_STATES);
+  for (int s = 0; s < S.n; ++s) {
+    S.geometry[s] = state_geometry[s];
+    S.density[s] = state_density[s]; S.energy[s] = state_energy[s];
+    S.xvel[s] = state_xvel[s]; S.yvel[s] = state_yvel[s];
+    S.xmin[s] = state_xmin[s]; S.xmax[s] = state_xmax[s];
+    S.ymin[s] = state_ymin[s]; S.ymax[s] = state_ymax[s];
+    S.radius[s] = state_radius[s];
+  }
+  S.g_rect = *g_rect; S.g_circ = *g_circ; S.g_point = *g_point;
+  const double* vx = dev(g, vertexx, X1D_VERT, IN);
+  const double* vy = dev(g, vertexy, Y1D_VERT, IN);
+  const double* cx = dev(g, cellx, X1D_CELL, IN);
+  const double* cy = dev(g, celly, Y1D_CELL, IN);
+  double* d0 = dev(g, density0, CELL, OUT);
+  double* e0 = dev(g, energy0, CELL, OUT);
+  double* x0 = dev(g, xvel0, VERTEX, OUT);
+  double* y0 = dev(g, yvel0, VERTEX, OUT);
+  {
+    const dim3 block(32, 8), grid((unsigned)((g.nx + 4 + XOFF + 32) / 32), (unsigned)((g.ny + 5 + 7) / 8));
+    LaunchScope ls("generate_chunk");
+    generate_chunk_kernel<<<grid, block, 0, stream()>>>(S, g.nx, g.ny, g.pitch, vx, vy, cx, cy, d0, e0, x0, y0);
+  }
+  finish();
+}
+
+}  // extern "C"

@@ -1,0 +1,553 @@
+// lagrange.cu -- the Lagrangian-phase kernels and the two reductions, fp64 CUDA for sm_100a:
+//   ideal_gas, viscosity, calc_dt (min-reduction), PdV predictor/corrector, revert, accelerate,
+//   flux_calc, reset_field, field_summary (sum-reductions).
+//
+// Numerics: built with -fmad=false; every expression keeps the evaluation order of the reference's
+// C source (cited per kernel) so fields are bit-identical to CloverLeaf_ref's C kernels compiled
+// with -ffp-contract=off.  Reductions: min is order-independent; sums use a fixed tree
+// (deterministic for a given mesh, differs from a serial CPU sum in the last bits only).
+//
+// Mapping: one thread per cell / vertex, threadIdx.x along j (unit stride, 128-byte aligned rows,
+// see common.cuh), 32x8 thread tiles; stencil neighbours come through L1.  All kernels here are
+// HBM-bound streaming passes; the algorithmic bytes per cell are listed in DESIGN.md.
+#include "clover_b200.h"
+#include "common.cuh"
+
+namespace clv {
+
+constexpr int BX = 32, BY = 8;
+
+struct Range {
+  int j0, j1, k0, k1;  // inclusive
+  int jbase;           // first column handled by block x = 0 (16-double aligned)
+};
+
+static inline Range make_range(int j0, int j1, int k0, int k1) {
+  Range r{j0, j1, k0, k1, 0};
+  r.jbase = ((j0 + XOFF) & ~15) - XOFF;
+  return r;
+}
+static inline dim3 grid_for(const Range& r) {
+  return dim3((unsigned)((r.j1 - r.jbase + 1 + BX - 1) / BX), (unsigned)((r.k1 - r.k0 + 1 + BY - 1) / BY), 1);
+}
+#define CLV_THREAD_JK(r)                                                  \
+  const int j = (r).jbase + (int)(blockIdx.x * BX + threadIdx.x);         \
+  const int k = (r).k0 + (int)(blockIdx.y * BY + threadIdx.y);            \
+  const bool active = (j >= (r).j0) && (j <= (r).j1) && (k <= (r).k1)
+
+// ------------------------------------------------------------------------------------------------
+// ideal_gas_kernel_c.c:48-59.  4 passes (2 reads, 2 writes) = 32 B/cell.
+__global__ void __launch_bounds__(BX* BY)
+    ideal_gas_kernel(Range r, int pitch, const double* __restrict__ density,
+                     const double* __restrict__ energy, double* __restrict__ pressure,
+                     double* __restrict__ soundspeed) {
+  CLV_THREAD_JK(r);
+  if (!active) return;
+  const size_t c = idx2(pitch, j, k);
+  const double rho = density[c];
+  const double v = 1.0 / rho;
+  const double p = (1.4 - 1.0) * rho * energy[c];
+  const double pe = (1.4 - 1.0) * rho;
+  const double pv = -rho * p;
+  const double ss2 = v * v * (p * pe - pv);
+  pressure[c] = p;
+  soundspeed[c] = sqrt(ss2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// viscosity_kernel_c.c:53-104.  5 passes = 40 B/cell.
+__global__ void __launch_bounds__(BX* BY)
+    viscosity_kernel(Range r, int pitch, const double* __restrict__ celldx,
+                     const double* __restrict__ celldy, const double* __restrict__ density0,
+                     const double* __restrict__ pressure, double* __restrict__ viscosity,
+                     const double* __restrict__ xvel0, const double* __restrict__ yvel0) {
+  CLV_THREAD_JK(r);
+  if (!active) return;
+  const size_t c = idx2(pitch, j, k);
+  const double u00 = xvel0[c], u10 = xvel0[c + 1], u01 = xvel0[c + pitch], u11 = xvel0[c + pitch + 1];
+  const double v00 = yvel0[c], v10 = yvel0[c + 1], v01 = yvel0[c + pitch], v11 = yvel0[c + pitch + 1];
+  const double dx = celldx[j + 1], dy = celldy[k + 1];
+  const double ugrad = (u10 + u11) - (u00 + u01);
+  const double vgrad = (v01 + v11) - (v00 + v10);
+  const double div = dx * ugrad + dy * vgrad;
+  const double strain2 = 0.5 * (u01 + u11 - u00 - u10) / dy + 0.5 * (v10 + v11 - v00 - v01) / dx;
+  double pgradx = (pressure[c + 1] - pressure[c - 1]) / (dx + celldx[j + 2]);
+  double pgrady = (pressure[c + pitch] - pressure[c - pitch]) / (dy + celldy[k + 2]);
+  const double pgradx2 = pgradx * pgradx, pgrady2 = pgrady * pgrady;
+  const double limiter =
+      ((0.5 * ugrad / dx) * pgradx2 + (0.5 * vgrad / dy) * pgrady2 + strain2 * pgradx * pgrady) /
+      dmax(pgradx2 + pgrady2, 1.0e-16);
+  double q = 0.0;
+  if (!(limiter > 0.0 || div >= 0.0)) {
+    const double ax = dmax(1.0e-16, fabs(pgradx)), ay = dmax(1.0e-16, fabs(pgrady));
+    pgradx = (pgradx < 0.0) ? -ax : ax;
+    pgrady = (pgrady < 0.0) ? -ay : ay;
+    const double pgrad = sqrt(pgradx * pgradx + pgrady * pgrady);
+    const double xgrad = fabs(dx * pgrad / pgradx);
+    const double ygrad = fabs(dy * pgrad / pgrady);
+    const double grad = dmin(xgrad, ygrad);
+    const double grad2 = grad * grad;
+    q = 2.0 * density0[c] * grad2 * limiter * limiter;
+  }
+  viscosity[c] = q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block-level reduction tails shared by calc_dt and field_summary: every block publishes its
+// partial(s), the last block to arrive (ticket) folds them in a fixed order and writes the result
+// to pinned host memory, then re-arms the ticket.
+template <int N, bool IS_MIN>
+__device__ __forceinline__ void block_reduce_publish(double (&v)[N], double* __restrict__ partials,
+                                                     unsigned int* ticket, double* __restrict__ out,
+                                                     double identity) {
+  __shared__ double sm[N][BX * BY / 32];
+  __shared__ bool last;
+  const int tid = threadIdx.y * BX + threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const unsigned nblocks = gridDim.x * gridDim.y;
+  const unsigned bid = blockIdx.y * gridDim.x + blockIdx.x;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double w = IS_MIN ? warp_min(v[i]) : warp_sum(v[i]);
+    if (lane == 0) sm[i][warp] = w;
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double a = sm[i][0];
+      for (int w = 1; w < BX * BY / 32; ++w) a = IS_MIN ? ((sm[i][w] < a) ? sm[i][w] : a) : a + sm[i][w];
+      partials[(size_t)i * nblocks + bid] = a;
+    }
+    __threadfence();
+    const unsigned t = atomicAdd(ticket, 1u);
+    last = (t == nblocks - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double a = identity;
+    for (unsigned b = tid; b < nblocks; b += BX * BY) {
+      const double p = __ldcg(&partials[(size_t)i * nblocks + b]);
+      a = IS_MIN ? ((p < a) ? p : a) : a + p;
+    }
+    a = IS_MIN ? warp_min(a) : warp_sum(a);
+    if (lane == 0) sm[i][warp] = a;
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double a = sm[i][0];
+      for (int w = 1; w < BX * BY / 32; ++w) a = IS_MIN ? ((sm[i][w] < a) ? sm[i][w] : a) : a + sm[i][w];
+      out[i] = a;
+    }
+    *ticket = 0;
+    __threadfence_system();
+  }
+}
+
+// calc_dt_kernel_c.c:96-144.  8 passes read = 64 B/cell; no per-cell dt_min array is written.
+struct DtParams {
+  double g_small, g_big, dtc_safe, dtu_safe, dtv_safe, dtdiv_safe;
+};
+__global__ void __launch_bounds__(BX* BY)
+    calc_dt_kernel(Range r, int pitch, DtParams P, const double* __restrict__ xarea,
+                   const double* __restrict__ yarea, const double* __restrict__ celldx,
+                   const double* __restrict__ celldy, const double* __restrict__ volume,
+                   const double* __restrict__ density0, const double* __restrict__ viscosity,
+                   const double* __restrict__ soundspeed, const double* __restrict__ xvel0,
+                   const double* __restrict__ yvel0, double* __restrict__ partials,
+                   unsigned int* ticket, double* __restrict__ out) {
+  CLV_THREAD_JK(r);
+  double m[1] = {P.g_big};
+  if (active) {
+    const size_t c = idx2(pitch, j, k);
+    const double dsx = celldx[j + 1], dsy = celldy[k + 1];
+    const double vol = volume[c];
+    double cc = soundspeed[c] * soundspeed[c];
+    cc = cc + 2.0 * viscosity[c] / density0[c];
+    cc = dmax(sqrt(cc), P.g_small);
+    const double dtct = P.dtc_safe * dmin(dsx, dsy) / cc;
+    double div = 0.0;
+    double dv1 = (xvel0[c] + xvel0[c + pitch]) * xarea[c];
+    double dv2 = (xvel0[c + 1] + xvel0[c + pitch + 1]) * xarea[c + 1];
+    div = div + dv2 - dv1;
+    const double dtut = P.dtu_safe * 2.0 * vol / dmax(fabs(dv1), dmax(fabs(dv2), P.g_small * vol));
+    dv1 = (yvel0[c] + yvel0[c + 1]) * yarea[c];
+    dv2 = (yvel0[c + pitch] + yvel0[c + pitch + 1]) * yarea[c + pitch];
+    div = div + dv2 - dv1;
+    const double dtvt = P.dtv_safe * 2.0 * vol / dmax(fabs(dv1), dmax(fabs(dv2), P.g_small * vol));
+    div = div / (2.0 * vol);
+    const double dtdivt = (div < -P.g_small) ? P.dtdiv_safe * (-1.0 / div) : P.g_big;
+    m[0] = dmin(dtct, dmin(dtut, dmin(dtvt, dtdivt)));
+  }
+  block_reduce_publish<1, true>(m, partials, ticket, out, P.g_big);
+}
+
+// field_summary_kernel_c.c:66-89.  6 passes read = 48 B/cell.
+__global__ void __launch_bounds__(BX* BY)
+    field_summary_kernel(Range r, int pitch, const double* __restrict__ volume,
+                         const double* __restrict__ density0, const double* __restrict__ energy0,
+                         const double* __restrict__ pressure, const double* __restrict__ xvel0,
+                         const double* __restrict__ yvel0, double* __restrict__ partials,
+                         unsigned int* ticket, double* __restrict__ out) {
+  CLV_THREAD_JK(r);
+  double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // vol, mass, ie, ke, press
+  if (active) {
+    const size_t c = idx2(pitch, j, k);
+    double vsqrd = 0.0;
+    vsqrd = vsqrd + 0.25 * (xvel0[c] * xvel0[c] + yvel0[c] * yvel0[c]);
+    vsqrd = vsqrd + 0.25 * (xvel0[c + 1] * xvel0[c + 1] + yvel0[c + 1] * yvel0[c + 1]);
+    vsqrd = vsqrd + 0.25 * (xvel0[c + pitch] * xvel0[c + pitch] + yvel0[c + pitch] * yvel0[c + pitch]);
+    vsqrd = vsqrd + 0.25 * (xvel0[c + pitch + 1] * xvel0[c + pitch + 1] + yvel0[c + pitch + 1] * yvel0[c + pitch + 1]);
+    const double cell_vol = volume[c];
+    const double cell_mass = cell_vol * density0[c];
+    s[0] = cell_vol;
+    s[1] = cell_mass;
+    s[2] = cell_mass * energy0[c];
+    s[3] = cell_mass * 0.5 * vsqrd;
+    s[4] = cell_vol * pressure[c];
+  }
+  block_reduce_publish<5, false>(s, partials, ticket, out, 0.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// PdV_kernel_c.c:63-113 (predictor) / :115-167 (corrector).  11 / 13 passes.
+template <bool PREDICT>
+__global__ void __launch_bounds__(BX* BY)
+    pdv_kernel(Range r, int pitch, double dt, const double* __restrict__ xarea,
+               const double* __restrict__ yarea, const double* __restrict__ volume,
+               const double* __restrict__ density0, double* __restrict__ density1,
+               const double* __restrict__ energy0, double* __restrict__ energy1,
+               const double* __restrict__ pressure, const double* __restrict__ viscosity,
+               const double* __restrict__ xvel0, const double* __restrict__ xvel1,
+               const double* __restrict__ yvel0, const double* __restrict__ yvel1) {
+  CLV_THREAD_JK(r);
+  if (!active) return;
+  const size_t c = idx2(pitch, j, k);
+  const double x00 = xvel0[c], x10 = xvel0[c + 1], x01 = xvel0[c + pitch], x11 = xvel0[c + pitch + 1];
+  const double y00 = yvel0[c], y10 = yvel0[c + 1], y01 = yvel0[c + pitch], y11 = yvel0[c + pitch + 1];
+  double left, right, bottom, top;
+  if (PREDICT) {
+    left = xarea[c] * (x00 + x01 + x00 + x01) * 0.25 * dt * 0.5;
+    right = xarea[c + 1] * (x10 + x11 + x10 + x11) * 0.25 * dt * 0.5;
+    bottom = yarea[c] * (y00 + y10 + y00 + y10) * 0.25 * dt * 0.5;
+    top = yarea[c + pitch] * (y01 + y11 + y01 + y11) * 0.25 * dt * 0.5;
+  } else {
+    const double a00 = xvel1[c], a10 = xvel1[c + 1], a01 = xvel1[c + pitch], a11 = xvel1[c + pitch + 1];
+    const double b00 = yvel1[c], b10 = yvel1[c + 1], b01 = yvel1[c + pitch], b11 = yvel1[c + pitch + 1];
+    left = xarea[c] * (x00 + x01 + a00 + a01) * 0.25 * dt;
+    right = xarea[c + 1] * (x10 + x11 + a10 + a11) * 0.25 * dt;
+    bottom = yarea[c] * (y00 + y10 + b00 + b10) * 0.25 * dt;
+    top = yarea[c + pitch] * (y01 + y11 + b01 + b11) * 0.25 * dt;
+  }
+  const double total = right - left + top - bottom;
+  const double vol = volume[c];
+  const double vc = vol / (vol + total);
+  const double recip = 1.0 / vol;
+  const double rho0 = density0[c];
+  const double de = (pressure[c] / rho0 + viscosity[c] / rho0) * total * recip;
+  energy1[c] = energy0[c] - de;
+  density1[c] = rho0 * vc;
+}
+
+// revert_kernel_c.c:46-62 (2 copies) and reset_field_kernel_c.c:46-76 (4 copies)
+__global__ void __launch_bounds__(BX* BY)
+    copy2_kernel(Range r, int pitch, const double* __restrict__ a_src, double* __restrict__ a_dst,
+                 const double* __restrict__ b_src, double* __restrict__ b_dst) {
+  CLV_THREAD_JK(r);
+  if (!active) return;
+  const size_t c = idx2(pitch, j, k);
+  a_dst[c] = a_src[c];
+  b_dst[c] = b_src[c];
+}
+__global__ void __launch_bounds__(BX* BY)
+    reset_field_kernel(Range r, int pitch, int nx, int ny, double* __restrict__ density0,
+                       const double* __restrict__ density1, double* __restrict__ energy0,
+                       const double* __restrict__ energy1, double* __restrict__ xvel0,
+                       const double* __restrict__ xvel1, double* __restrict__ yvel0,
+                       const double* __restrict__ yvel1) {
+  CLV_THREAD_JK(r);
+  if (!active) return;
+  const size_t c = idx2(pitch, j, k);
+  if (j <= nx && k <= ny) {
+    density0[c] = density1[c];
+    energy0[c] = energy1[c];
+  }
+  xvel0[c] = xvel1[c];
+  yvel0[c] = yvel1[c];
+}
+
+// accelerate_kernel_c.c:56-95.  10 passes = 80 B/cell.
+__global__ void __launch_bounds__(BX* BY)
+    accelerate_kernel(Range r, int pitch, double dt, const double* __restrict__ xarea,
+                      const double* __restrict__ yarea, const double* __restrict__ volume,
+                      const double* __restrict__ density0, const double* __restrict__ pressure,
+                      const double* __restrict__ viscosity, const double* __restrict__ xvel0,
+                      const double* __restrict__ yvel0, double* __restrict__ xvel1,
+                      double* __restrict__ yvel1) {
+  CLV_THREAD_JK(r);
+  if (!active) return;
+  const size_t c11 = idx2(pitch, j, k), c01 = c11 - 1, c10 = c11 - pitch, c00 = c10 - 1;
+  const double nodal_mass = (density0[c00] * volume[c00] + density0[c10] * volume[c10] +
+                             density0[c11] * volume[c11] + density0[c01] * volume[c01]) * 0.25;
+  const double s = 0.5 * dt / nodal_mass;
+  const double xa1 = xarea[c11], xa0 = xarea[c10];
+  const double ya1 = yarea[c11], ya0 = yarea[c01];
+  const double p11 = pressure[c11], p01 = pressure[c01], p10 = pressure[c10], p00 = pressure[c00];
+  const double q11 = viscosity[c11], q01 = viscosity[c01], q10 = viscosity[c10], q00 = viscosity[c00];
+  double xv = xvel0[c11] - s * (xa1 * (p11 - p01) + xa0 * (p10 - p00));
+  double yv = yvel0[c11] - s * (ya1 * (p11 - p10) + ya0 * (p01 - p00));
+  xv = xv - s * (xa1 * (q11 - q01) + xa0 * (q10 - q00));
+  yv = yv - s * (ya1 * (q11 - q10) + ya0 * (q01 - q00));
+  xvel1[c11] = xv;
+  yvel1[c11] = yv;
+}
+
+// flux_calc_kernel_c.c:49-73.  8 passes = 64 B/cell.
+__global__ void __launch_bounds__(BX* BY)
+    flux_calc_kernel(Range r, int pitch, int nx, int ny, double dt, const double* __restrict__ xarea,
+                     const double* __restrict__ yarea, const double* __restrict__ xvel0,
+                     const double* __restrict__ yvel0, const double* __restrict__ xvel1,
+                     const double* __restrict__ yvel1, double* __restrict__ vol_flux_x,
+                     double* __restrict__ vol_flux_y) {
+  CLV_THREAD_JK(r);
+  if (!active) return;
+  const size_t c = idx2(pitch, j, k);
+  const double x0 = xvel0[c], x1 = xvel1[c], y0 = yvel0[c], y1 = yvel1[c];
+  if (k <= ny)
+    vol_flux_x[c] = 0.25 * dt * xarea[c] * (x0 + xvel0[c + pitch] + x1 + xvel1[c + pitch]);
+  if (j <= nx)
+    vol_flux_y[c] = 0.25 * dt * yarea[c] * (y0 + yvel0[c + 1] + y1 + yvel1[c + 1]);
+}
+
+}  // namespace clv
+
+using namespace clv;
+
+extern "C" {
+
+void ideal_gas_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* density, double* energy,
+                         double* pressure, double* soundspeed) {
+  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+  const double* d = dev(g, density, CELL, IN);
+  const double* e = dev(g, energy, CELL, IN);
+  double* p = dev(g, pressure, CELL, OUT);
+  double* ss = dev(g, soundspeed, CELL, OUT);
+  const Range r = make_range(1, g.nx, 1, g.ny);
+  {
+    LaunchScope ls("ideal_gas");
+    ideal_gas_kernel<<<grid_for(r), dim3(BX, BY), 0, stream()>>>(r, g.pitch, d, e, p, ss);
+  }
+  finish();
+}
+
+void viscosity_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* celldx, double* celldy,
+                         double* density0, double* pressure, double* viscosity, double* xvel0,
+                         double* yvel0) {
+  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+  const double* cdx = dev(g, celldx, X1D_CELL, IN);
+  const double* cdy = dev(g, celldy, Y1D_CELL, IN);
+  const double* d0 = dev(g, density0, CELL, IN);
+  const double* p = dev(g, pressure, CELL, IN);
+  double* q = dev(g, viscosity, CELL, OUT);
+  const double* xv = dev(g, xvel0, VERTEX, IN);
+  const double* yv = dev(g, yvel0, VERTEX, IN);
+  const Range r = make_range(1, g.nx, 1, g.ny);
+  {
+    LaunchScope ls("viscosity");
+    viscosity_kernel<<<grid_for(r), dim3(BX, BY), 0, stream()>>>(r, g.pitch, cdx, cdy, d0, p, q, xv, yv);
+  }
+  finish();
+}
+
+void calc_dt_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* g_small, double* g_big,
+                       double* dtmin, double* dtc_safe, double* dtu_safe, double* dtv_safe,
+                       double* dtdiv_safe, double* xarea, double* yarea, double* cellx, double* celly,
+                       double* celldx, double* celldy, double* volume, double* density0,
+                       double* energy0, double* pressure, double* viscosity, double* soundspeed,
+                       double* xvel0, double* yvel0, double* dt_min, double* dt_min_val,
+                       int* dtl_control, double* xl_pos, double* yl_pos, int* jldt, int* kldt,
+                       int* small) {
+  (void)cellx; (void)celly; (void)energy0; (void)pressure; (void)dt_min; (void)xl_pos; (void)yl_pos;
+  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+  const double* xa = dev(g, xarea, XFACE, IN);
+  const double* ya = dev(g, yarea, YFACE, IN);
+  const double* cdx = dev(g, celldx, X1D_CELL, IN);
+  const double* cdy = dev(g, celldy, Y1D_CELL, IN);
+  const double* vol = dev(g, volume, CELL, IN);
+  const double* d0 = dev(g, density0, CELL, IN);
+  const double* q = dev(g, viscosity, CELL, IN);
+  const double* ss = dev(g, soundspeed, CELL, IN);
+  const double* xv = dev(g, xvel0, VERTEX, IN);
+  const double* yv = dev(g, yvel0, VERTEX, IN);
+  const Range r = make_range(1, g.nx, 1, g.ny);
+  const dim3 grid = grid_for(r);
+  double* part = partials((size_t)grid.x * grid.y);
+  DtParams P{*g_small, *g_big, *dtc_safe, *dtu_safe, *dtv_safe, *dtdiv_safe};
+  double* out = host_scalars();
+  {
+    LaunchScope ls("calc_dt");
+    calc_dt_kernel<<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, P, xa, ya, cdx, cdy, vol, d0, q, ss, xv,
+                                                        yv, part, ticket(), out);
+  }
+  CLV_CUDA(cudaStreamSynchronize(stream()));  // the one unavoidable host-visible result per step
+  const double v = out[0];
+  *dt_min_val = v;
+  *dtl_control = 1;  // calc_dt_kernel_c.c:159-163
+  *jldt = 1;
+  *kldt = 1;
+  if (v < *dtmin) {
+    if (small) *small = 1;
+    printf("Timestep information:\ntimestep : %f (below dtmin)\n", v);
+  }
+  finish();
+}
+
+void pdv_kernel_c_(int* prdct, int* xmin, int* xmax, int* ymin, int* ymax, double* dt, double* xarea,
+                   double* yarea, double* volume, double* density0, double* density1, double* energy0,
+                   double* energy1, double* pressure, double* viscosity, double* xvel0, double* xvel1,
+                   double* yvel0, double* yvel1, double* volume_change) {
+  (void)volume_change;
+  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+  const bool predict = (*prdct == 0);
+  const double* xa = dev(g, xarea, XFACE, IN);
+  const double* ya = dev(g, yarea, YFACE, IN);
+  const double* vol = dev(g, volume, CELL, IN);
+  const double* d0 = dev(g, density0, CELL, IN);
+  double* d1 = dev(g, density1, CELL, OUT);
+  const double* e0 = dev(g, energy0, CELL, IN);
+  double* e1 = dev(g, energy1, CELL, OUT);
+  const double* p = dev(g, pressure, CELL, IN);
+  const double* q = dev(g, viscosity, CELL, IN);
+  const double* x0 = dev(g, xvel0, VERTEX, IN);
+  const double* y0 = dev(g, yvel0, VERTEX, IN);
+  const Range r = make_range(1, g.nx, 1, g.ny);
+  if (predict) {
+    LaunchScope ls("pdv_predict");
+    pdv_kernel<true><<<grid_for(r), dim3(BX, BY), 0, stream()>>>(r, g.pitch, *dt, xa, ya, vol, d0, d1, e0, e1, p,
+                                                                q, x0, x0, y0, y0);
+  } else {
+    const double* x1 = dev(g, xvel1, VERTEX, IN);
+    const double* y1 = dev(g, yvel1, VERTEX, IN);
+    LaunchScope ls("pdv_correct");
+    pdv_kernel<false><<<grid_for(r), dim3(BX, BY), 0, stream()>>>(r, g.pitch, *dt, xa, ya, vol, d0, d1, e0, e1,
+                                                                 p, q, x0, x1, y0, y1);
+  }
+  finish();
+}
+
+void revert_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* density0, double* density1,
+                      double* energy0, double* energy1) {
+  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+  const double* d0 = dev(g, density0, CELL, IN);
+  double* d1 = dev(g, density1, CELL, OUT);
+  const double* e0 = dev(g, energy0, CELL, IN);
+  double* e1 = dev(g, energy1, CELL, OUT);
+  const Range r = make_range(1, g.nx, 1, g.ny);
+  {
+    LaunchScope ls("revert");
+    copy2_kernel<<<grid_for(r), dim3(BX, BY), 0, stream()>>>(r, g.pitch, d0, d1, e0, e1);
+  }
+  finish();
+}
+
+void reset_field_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* density0,
+                           double* density1, double* energy0, double* energy1, double* xvel0,
+                           double* xvel1, double* yvel0, double* yvel1) {
+  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+  double* d0 = dev(g, density0, CELL, OUT);
+  const double* d1 = dev(g, density1, CELL, IN);
+  double* e0 = dev(g, energy0, CELL, OUT);
+  const double* e1 = dev(g, energy1, CELL, IN);
+  double* x0 = dev(g, xvel0, VERTEX, OUT);
+  const double* x1 = dev(g, xvel1, VERTEX, IN);
+  double* y0 = dev(g, yvel0, VERTEX, OUT);
+  const double* y1 = dev(g, yvel1, VERTEX, IN);
+  const Range r = make_range(1, g.nx + 1, 1, g.ny + 1);
+  {
+    LaunchScope ls("reset_field");
+    reset_field_kernel<<<grid_for(r), dim3(BX, BY), 0, stream()>>>(r, g.pitch, g.nx, g.ny, d0, d1, e0, e1, x0,
+                                                                  x1, y0, y1);
+  }
+  finish();
+}
+
+void accelerate_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* dt, double* xarea,
+                          double* yarea, double* volume, double* density0, double* pressure,
+                          double* viscosity, double* xvel0, double* yvel0, double* xvel1,
+                          double* yvel1) {
+  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+  const double* xa = dev(g, xarea, XFACE, IN);
+  const double* ya = dev(g, yarea, YFACE, IN);
+  const double* vol = dev(g, volume, CELL, IN);
+  const double* d0 = dev(g, density0, CELL, IN);
+  const double* p = dev(g, pressure, CELL, IN);
+  const double* q = dev(g, viscosity, CELL, IN);
+  const double* x0 = dev(g, xvel0, VERTEX, IN);
+  const double* y0 = dev(g, yvel0, VERTEX, IN);
+  double* x1 = dev(g, xvel1, VERTEX, OUT);
+  double* y1 = dev(g, yvel1, VERTEX, OUT);
+  const Range r = make_range(1, g.nx + 1, 1, g.ny + 1);
+  {
+    LaunchScope ls("accelerate");
+    accelerate_kernel<<<grid_for(r), dim3(BX, BY), 0, stream()>>>(r, g.pitch, *dt, xa, ya, vol, d0, p, q, x0, y0,
+                                                                 x1, y1);
+  }
+  finish();
+}
+
+void flux_calc_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* dt, double* xarea,
+                         double* yarea, double* xvel0, double* yvel0, double* xvel1, double* yvel1,
+                         double* vol_flux_x, double* vol_flux_y) {
+  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+  const double* xa = dev(g, xarea, XFACE, IN);
+  const double* ya = dev(g, yarea, YFACE, IN);
+  const double* x0 = dev(g, xvel0, VERTEX, IN);
+  const double* y0 = dev(g, yvel0, VERTEX, IN);
+  const double* x1 = dev(g, xvel1, VERTEX, IN);
+  const double* y1 = dev(g, yvel1, VERTEX, IN);
+  double* fx = dev(g, vol_flux_x, XFACE, OUT);
+  double* fy = dev(g, vol_flux_y, YFACE, OUT);
+  const Range r = make_range(1, g.nx + 1, 1, g.ny + 1);
+  {
+    LaunchScope ls("flux_calc");
+    flux_calc_kernel<<<grid_for(r), dim3(BX, BY), 0, stream()>>>(r, g.pitch, g.nx, g.ny, *dt, xa, ya, x0, y0, x1,
+                                                                y1, fx, fy);
+  }
+  finish();
+}
+
+void field_summary_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* volume,
+                             double* density0, double* energy0, double* pressure, double* xvel0,
+                             double* yvel0, double* vol, double* mass, double* ie, double* ke,
+                             double* press) {
+  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+  const double* v = dev(g, volume, CELL, IN);
+  const double* d0 = dev(g, density0, CELL, IN);
+  const double* e0 = dev(g, energy0, CELL, IN);
+  const double* p = dev(g, pressure, CELL, IN);
+  const double* x0 = dev(g, xvel0, VERTEX, IN);
+  const double* y0 = dev(g, yvel0, VERTEX, IN);
+  const Range r = make_range(1, g.nx, 1, g.ny);
+  const dim3 grid = grid_for(r);
+  double* part = partials((size_t)grid.x * grid.y * 5);
+  double* out = host_scalars() + 8;
+  {
+    LaunchScope ls("field_summary");
+    field_summary_kernel<<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, v, d0, e0, p, x0, y0, part,
+                                                              ticket() + 1, out);
+  }
+  CLV_CUDA(cudaStreamSynchronize(stream()));
+  *vol = out[0];
+  *mass = out[1];
+  *ie = out[2];
+  *ke = out[3];
+  *press = out[4];
+  finish();
+}
+
+}  // extern "C"

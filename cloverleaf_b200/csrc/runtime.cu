@@ -1,0 +1,441 @@
+// runtime.cu -- device residency, streams, bookkeeping and the non-kernel extension entry points
+// of libclover_b200.so.  See include/clover_b200.h for the ABI and common.cuh for the layout.
+#include <sys/time.h>
+
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "clover_b200.h"
+#include "common.cuh"
+
+namespace clv {
+
+[[noreturn]] void fatal(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  fprintf(stderr, "libclover_b200: fatal: ");
+  vfprintf(stderr, fmt, ap);
+  fprintf(stderr, "\n");
+  va_end(ap);
+  abort();
+}
+
+namespace {
+
+struct Entry {
+  double* d = nullptr;
+  double* alt = nullptr;
+  Kind kind = CELL;
+  int nx = 0, ny = 0;
+  size_t doubles = 0;
+};
+
+struct Buffer {
+  double* d = nullptr;
+  size_t doubles = 0;
+};
+
+struct Prof {
+  double ms = 0;
+  long long calls = 0;
+};
+
+struct Runtime {
+  bool ready = false;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool resident = true;
+  std::unordered_map<const void*, Entry> arrays;
+  std::unordered_map<const void*, Buffer> buffers;
+  std::vector<const void*> pending_out;  // non-resident mode: arrays to download in finish()
+  double* h_scalars = nullptr;           // pinned + mapped
+  double* d_partials = nullptr;
+  size_t partials_doubles = 0;
+  unsigned int* d_ticket = nullptr;
+  long long launches = 0;
+  long long h2d = 0, d2h = 0;
+  bool profiling = false;
+  std::map<std::string, Prof> prof;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+Runtime R;
+
+bool is_2d(Kind k) { return k <= YFACE; }
+int host_row(Kind k, int nx) { return (k == CELL || k == YFACE) ? nx + 4 : nx + 5; }
+int host_rows(Kind k, int ny) { return (k == CELL || k == XFACE) ? ny + 4 : ny + 5; }
+size_t len_1d(Kind k, int nx, int ny) {
+  switch (k) {
+    case X1D_CELL: return nx + 4;
+    case X1D_VERT: return nx + 5;
+    case Y1D_CELL: return ny + 4;
+    default: return ny + 5;
+  }
+}
+
+void upload(const Entry& e, const double* host) {
+  if (is_2d(e.kind)) {
+    const int pitch = pitch_for(e.nx);
+    const size_t w = (size_t)host_row(e.kind, e.nx) * sizeof(double);
+    const size_t h = host_rows(e.kind, e.ny);
+    CLV_CUDA(cudaMemcpy2DAsync(e.d + (XOFF - 1), (size_t)pitch * sizeof(double), host, w, w, h,
+                               cudaMemcpyHostToDevice, R.stream));
+    R.h2d += (long long)(w * h);
+  } else {
+    const size_t n = len_1d(e.kind, e.nx, e.ny) * sizeof(double);
+    CLV_CUDA(cudaMemcpyAsync(e.d, host, n, cudaMemcpyHostToDevice, R.stream));
+    R.h2d += (long long)n;
+  }
+}
+
+void download(const Entry& e, double* host) {
+  if (is_2d(e.kind)) {
+    const int pitch = pitch_for(e.nx);
+    const size_t w = (size_t)host_row(e.kind, e.nx) * sizeof(double);
+    const size_t h = host_rows(e.kind, e.ny);
+    CLV_CUDA(cudaMemcpy2DAsync(host, w, e.d + (XOFF - 1), (size_t)pitch * sizeof(double), w, h,
+                               cudaMemcpyDeviceToHost, R.stream));
+    R.d2h += (long long)(w * h);
+  } else {
+    const size_t n = len_1d(e.kind, e.nx, e.ny) * sizeof(double);
+    CLV_CUDA(cudaMemcpyAsync(host, e.d, n, cudaMemcpyDeviceToHost, R.stream));
+    R.d2h += (long long)n;
+  }
+}
+
+double* alloc_zeroed(size_t doubles) {
+  double* p = nullptr;
+  CLV_CUDA(cudaMalloc(&p, doubles * sizeof(double)));
+  CLV_CUDA(cudaMemsetAsync(p, 0, doubles * sizeof(double), R.stream));
+  return p;
+}
+
+size_t doubles_for(Kind kind, int nx, int ny) {
+  // uniform 2-D shape: (ny+5) rows of `pitch`, plus a row of slack so that clamped halo threads
+  // of the sweep kernels can never leave the allocation
+  if (is_2d(kind)) return (size_t)pitch_for(nx) * (size_t)(ny + 6);
+  return len_1d(kind, nx, ny) + 8;
+}
+
+// The chunk registered for exchange / sync_to_host (one chunk per process == per GPU)
+struct Chunk {
+  bool set = false;
+  int nx = 0, ny = 0;
+  int neighbours[4] = {-1, -1, -1, -1};
+  double* field[15] = {};
+} C;
+
+}  // namespace
+
+void ensure_init() {
+  if (R.ready) return;
+  int dev_id = 0;
+  if (const char* s = getenv("CLOVER_B200_DEVICE")) dev_id = atoi(s);
+  clover_b200_init_(&dev_id);
+}
+
+cudaStream_t stream() { return R.stream; }
+
+Grid grid_of(const int* xmin, const int* xmax, const int* ymin, const int* ymax) {
+  ensure_init();
+  if (*xmin != 1 || *ymin != 1)
+    fatal("x_min/y_min must be 1 (start.f90:77-80 always passes 1), got %d/%d", *xmin, *ymin);
+  if (*xmax < 1 || *ymax < 1) fatal("empty chunk %d x %d", *xmax, *ymax);
+  Grid g;
+  g.nx = *xmax;
+  g.ny = *ymax;
+  g.pitch = pitch_for(g.nx);
+  return g;
+}
+
+static Entry& lookup(const Grid& g, const double* host, Kind kind, bool* fresh) {
+  if (!host) fatal("null array pointer passed to a kernel entry point");
+  auto it = R.arrays.find(host);
+  if (it != R.arrays.end()) {
+    Entry& e = it->second;
+    if (e.kind == kind && e.nx == g.nx && e.ny == g.ny) {
+      *fresh = false;
+      return e;
+    }
+    // same host address re-used with another shape (e.g. a work array): re-create the mirror
+    CLV_CUDA(cudaStreamSynchronize(R.stream));
+    CLV_CUDA(cudaFree(e.d));
+    if (e.alt) CLV_CUDA(cudaFree(e.alt));
+    R.arrays.erase(it);
+  }
+  Entry e;
+  e.kind = kind;
+  e.nx = g.nx;
+  e.ny = g.ny;
+  e.doubles = doubles_for(kind, g.nx, g.ny);
+  e.d = alloc_zeroed(e.doubles);
+  *fresh = true;
+  return R.arrays.emplace(host, e).first->second;
+}
+
+double* dev(const Grid& g, const double* host, Kind kind, int access) {
+  bool fresh = false;
+  Entry& e = lookup(g, host, kind, &fresh);
+  // Resident mode: the host copy is authoritative only the first time the address is seen.
+  // Copy-in/out mode: it is authoritative on every call (outputs too: a kernel writes only its
+  // loop range, the rest of the array must survive the round trip).
+  if (fresh || !R.resident) upload(e, host);
+  if (!R.resident && (access & OUT)) R.pending_out.push_back(host);
+  return e.d;
+}
+
+double* dev_alt(const Grid& g, const double* host, Kind kind) {
+  bool fresh = false;
+  Entry& e = lookup(g, host, kind, &fresh);
+  if (fresh) upload(e, host);
+  if (!e.alt) e.alt = alloc_zeroed(e.doubles);
+  return e.alt;
+}
+
+void swap_alt(const double* host) {
+  auto it = R.arrays.find(host);
+  if (it == R.arrays.end() || !it->second.alt) fatal("swap_alt on an array without alt buffer");
+  std::swap(it->second.d, it->second.alt);
+}
+
+double* dev_buffer(const double* host, size_t need, int access, size_t lo, size_t hi) {
+  ensure_init();
+  if (!host) fatal("null message buffer");
+  Buffer& b = R.buffers[host];
+  if (b.doubles < need) {
+    size_t n = need + need / 2 + 64;
+    double* p = alloc_zeroed(n);
+    if (b.d) {
+      CLV_CUDA(cudaMemcpyAsync(p, b.d, b.doubles * sizeof(double), cudaMemcpyDeviceToDevice, R.stream));
+      CLV_CUDA(cudaStreamSynchronize(R.stream));
+      CLV_CUDA(cudaFree(b.d));
+    }
+    b.d = p;
+    b.doubles = n;
+  }
+  if ((access & IN) && hi > lo) {
+    CLV_CUDA(cudaMemcpyAsync(b.d + lo, host + lo, (hi - lo) * sizeof(double), cudaMemcpyHostToDevice, R.stream));
+    R.h2d += (long long)((hi - lo) * sizeof(double));
+  }
+  return b.d;
+}
+
+void finish() {
+  if (R.resident) return;
+  for (const void* h : R.pending_out) {
+    auto it = R.arrays.find(h);
+    if (it != R.arrays.end()) download(it->second, (double*)h);
+  }
+  R.pending_out.clear();
+  CLV_CUDA(cudaStreamSynchronize(R.stream));
+}
+
+LaunchScope::LaunchScope(const char* n) : name(n) {
+  if (R.profiling) CLV_CUDA(cudaEventRecord(R.ev0, R.stream));
+}
+LaunchScope::~LaunchScope() {
+  R.launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) fatal("launch of %s failed: %s", name, cudaGetErrorString(e));
+  if (R.profiling) {
+    CLV_CUDA(cudaEventRecord(R.ev1, R.stream));
+    CLV_CUDA(cudaEventSynchronize(R.ev1));
+    float ms = 0;
+    CLV_CUDA(cudaEventElapsedTime(&ms, R.ev0, R.ev1));
+    Prof& p = R.prof[name];
+    p.ms += ms;
+    p.calls++;
+  }
+}
+
+double* host_scalars() { return R.h_scalars; }
+unsigned int* ticket() { return R.d_ticket; }
+double* partials(size_t doubles) {
+  if (R.partials_doubles < doubles) {
+    if (R.d_partials) {
+      CLV_CUDA(cudaStreamSynchronize(R.stream));
+      CLV_CUDA(cudaFree(R.d_partials));
+    }
+    R.partials_doubles = doubles + 1024;
+    CLV_CUDA(cudaMalloc(&R.d_partials, R.partials_doubles * sizeof(double)));
+  }
+  return R.d_partials;
+}
+
+// used by halo.cu
+bool chunk_registered() { return C.set; }
+int chunk_nx() { return C.nx; }
+int chunk_ny() { return C.ny; }
+const int* chunk_neighbours() { return C.neighbours; }
+double* chunk_field_host(int f) { return C.field[f]; }
+void count_copy(long long h2d, long long d2h) { R.h2d += h2d; R.d2h += d2h; }
+
+}  // namespace clv
+
+using namespace clv;
+
+extern "C" {
+
+void clover_b200_init_(int* device) {
+  if (R.ready) return;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    fatal("no CUDA device available (%s); this library has no CPU fallback",
+          e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  R.device = device ? *device : 0;
+  if (R.device < 0 || R.device >= n) fatal("device %d out of range (%d devices)", R.device, n);
+  CLV_CUDA(cudaSetDevice(R.device));
+  cudaDeviceProp p;
+  CLV_CUDA(cudaGetDeviceProperties(&p, R.device));
+  if (p.major != 10)
+    fatal("device %d is sm_%d%d; this library is built for sm_100a (B200) only", R.device, p.major, p.minor);
+  CLV_CUDA(cudaStreamCreateWithFlags(&R.stream, cudaStreamNonBlocking));
+  CLV_CUDA(cudaHostAlloc(&R.h_scalars, 64 * sizeof(double), cudaHostAllocMapped));
+  CLV_CUDA(cudaMalloc(&R.d_ticket, 16 * sizeof(unsigned int)));
+  CLV_CUDA(cudaMemset(R.d_ticket, 0, 16 * sizeof(unsigned int)));
+  CLV_CUDA(cudaEventCreate(&R.ev0));
+  CLV_CUDA(cudaEventCreate(&R.ev1));
+  R.ready = true;
+}
+
+void clover_b200_comm_finalize_internal();
+
+void clover_b200_finalize_(void) {
+  if (!R.ready) return;
+  CLV_CUDA(cudaStreamSynchronize(R.stream));
+  clover_b200_comm_finalize_internal();
+  clover_b200_invalidate_();
+  if (R.d_partials) CLV_CUDA(cudaFree(R.d_partials));
+  R.d_partials = nullptr;
+  R.partials_doubles = 0;
+  CLV_CUDA(cudaFree(R.d_ticket));
+  CLV_CUDA(cudaFreeHost(R.h_scalars));
+  CLV_CUDA(cudaEventDestroy(R.ev0));
+  CLV_CUDA(cudaEventDestroy(R.ev1));
+  CLV_CUDA(cudaStreamDestroy(R.stream));
+  R.ready = false;
+  C = Chunk();
+}
+
+void clover_b200_set_resident_(int* on) {
+  ensure_init();
+  CLV_CUDA(cudaStreamSynchronize(R.stream));
+  R.resident = (*on != 0);
+}
+
+void clover_b200_invalidate_(void) {
+  if (!R.ready) return;
+  CLV_CUDA(cudaStreamSynchronize(R.stream));
+  for (auto& kv : R.arrays) {
+    CLV_CUDA(cudaFree(kv.second.d));
+    if (kv.second.alt) CLV_CUDA(cudaFree(kv.second.alt));
+  }
+  R.arrays.clear();
+  for (auto& kv : R.buffers) CLV_CUDA(cudaFree(kv.second.d));
+  R.buffers.clear();
+  R.pending_out.clear();
+}
+
+void clover_b200_forget_(double* host) {
+  if (!R.ready) return;
+  auto it = R.arrays.find(host);
+  if (it != R.arrays.end()) {
+    CLV_CUDA(cudaStreamSynchronize(R.stream));
+    CLV_CUDA(cudaFree(it->second.d));
+    if (it->second.alt) CLV_CUDA(cudaFree(it->second.alt));
+    R.arrays.erase(it);
+  }
+  auto ib = R.buffers.find(host);
+  if (ib != R.buffers.end()) {
+    CLV_CUDA(cudaStreamSynchronize(R.stream));
+    CLV_CUDA(cudaFree(ib->second.d));
+    R.buffers.erase(ib);
+  }
+}
+
+void clover_b200_upload_(double* host) {
+  ensure_init();
+  auto it = R.arrays.find(host);
+  if (it == R.arrays.end()) return;  // never seen: the first use uploads it anyway
+  upload(it->second, host);
+}
+
+void clover_b200_download_(double* host) {
+  ensure_init();
+  auto it = R.arrays.find(host);
+  if (it == R.arrays.end()) fatal("download of an array the library has never seen");
+  download(it->second, host);
+  CLV_CUDA(cudaStreamSynchronize(R.stream));
+}
+
+void clover_b200_sync_to_host_(int* fields) {
+  ensure_init();
+  if (!C.set) fatal("sync_to_host before register_chunk");
+  for (int f = 0; f < 15; ++f) {
+    if (fields && fields[f] != 1) continue;
+    auto it = R.arrays.find(C.field[f]);
+    if (it != R.arrays.end()) download(it->second, C.field[f]);
+  }
+  CLV_CUDA(cudaStreamSynchronize(R.stream));
+}
+
+void clover_b200_device_synchronize_(void) {
+  ensure_init();
+  CLV_CUDA(cudaStreamSynchronize(R.stream));
+}
+
+void clover_b200_register_chunk_(int* xmin, int* xmax, int* ymin, int* ymax, int* nb, double* density0,
+                                 double* density1, double* energy0, double* energy1, double* pressure,
+                                 double* viscosity, double* soundspeed, double* xvel0, double* xvel1,
+                                 double* yvel0, double* yvel1, double* vol_flux_x, double* vol_flux_y,
+                                 double* mass_flux_x, double* mass_flux_y) {
+  Grid g = grid_of(xmin, xmax, ymin, ymax);
+  C.set = true;
+  C.nx = g.nx;
+  C.ny = g.ny;
+  for (int i = 0; i < 4; ++i) C.neighbours[i] = nb[i];
+  // field ids of data.f90:51-66, zero-based
+  double* f[15] = {density0, density1, energy0, energy1, pressure, viscosity, soundspeed, xvel0,
+                   xvel1, yvel0, yvel1, vol_flux_x, vol_flux_y, mass_flux_x, mass_flux_y};
+  for (int i = 0; i < 15; ++i) C.field[i] = f[i];
+}
+
+void clover_b200_launch_count_(long long* n) { *n = R.launches; }
+
+void clover_b200_profile_(int* on) {
+  ensure_init();
+  R.profiling = (*on != 0);
+}
+
+void clover_b200_profile_reset_(void) { R.prof.clear(); }
+
+void clover_b200_profile_get_(int* max, char* names32, double* total_ms, long long* calls, int* n) {
+  int i = 0;
+  for (auto& kv : R.prof) {
+    if (i >= *max) break;
+    memset(names32 + 32 * i, 0, 32);
+    strncpy(names32 + 32 * i, kv.first.c_str(), 31);
+    total_ms[i] = kv.second.ms;
+    calls[i] = kv.second.calls;
+    ++i;
+  }
+  *n = i;
+}
+
+void clover_b200_copy_bytes_(long long* h2d, long long* d2h) {
+  *h2d = R.h2d;
+  *d2h = R.d2h;
+}
+
+void timer_c_(double* elapsed_time) {
+  struct timeval t;
+  gettimeofday(&t, nullptr);
+  *elapsed_time = t.tv_sec + t.tv_usec * 1.0E-6;
+}
+
+}  // extern "C"

@@ -12,27 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DRIVER = os.path.join(HERE, "libclover_driver.so")
 DECK_DIR = os.path.join(HERE, "decks")
 
-# The reference's C entry points -- the drop-in boundary.
-KERNEL_SYMBOLS = [
-    "ideal_gas_kernel_c_", "viscosity_kernel_c_", "calc_dt_kernel_c_", "pdv_kernel_c_",
-    "revert_kernel_c_", "accelerate_kernel_c_", "flux_calc_kernel_c_", "advec_cell_kernel_c_",
-    "advec_mom_kernel_c_", "reset_field_kernel_c_", "update_halo_kernel_c_",
-    "field_summary_kernel_c_", "initialise_chunk_kernel_c_", "generate_chunk_kernel_c_",
-    "clover_pack_message_left_c_", "clover_unpack_message_left_c_",
-    "clover_pack_message_right_c_", "clover_unpack_message_right_c_",
-    "clover_pack_message_top_c_", "clover_unpack_message_top_c_",
-    "clover_pack_message_bottom_c_", "clover_unpack_message_bottom_c_",
-]
-# GPU-backend extension (include/clover_b200.h)
-EXTENSION_SYMBOLS = [
-    "timer_c_",
-    "clover_b200_init_", "clover_b200_finalize_", "clover_b200_set_resident_",
-    "clover_b200_set_stream_", "clover_b200_invalidate_", "clover_b200_sync_to_host_",
-    "clover_b200_device_synchronize_", "clover_b200_register_chunk_",
-    "clover_b200_comm_get_unique_id_", "clover_b200_comm_init_", "clover_b200_exchange_",
-    "clover_b200_min_", "clover_b200_sum_", "clover_b200_timer_start_", "clover_b200_timer_stop_",
-    "clover_b200_launch_count_", "clover_b200_kernel_time_ms_",
-]
+from .abi import KERNEL_SYMBOLS, EXTENSION_SYMBOLS  # noqa: F401  (re-exported)
 
 _lib = None
 

@@ -1,0 +1,231 @@
+/* clover_b200.h -- C ABI of libclover_b200.so, the B200 (sm_100a) kernel layer for CloverLeaf.
+ *
+ * Part 1 is the drop-in boundary: the SAME Fortran-callable symbols that
+ * CloverLeaf_ref/kernels/ *_kernel_c.c export and that the L1 wrappers of CloverLeaf_ref call on
+ * the `use_c_kernels` path (implicit-interface external calls: lowercase name + trailing
+ * underscore, every argument by reference, INTEGER -> int*, REAL(KIND=8) -> double*, arrays ->
+ * pointer to the first element of the contiguous Fortran allocation whose lower bound is
+ * (x_min-2, y_min-2)).  All return void.  Array arguments are HOST pointers; the library keeps a
+ * device-resident mirror of every array it has seen, keyed by the host address (Fortran allocates
+ * each field once, build_field.f90:33-94, and never moves it).
+ *
+ * Part 2 is the small extension a GPU backend needs and the reference ABI has no word for:
+ * residency control, host synchronisation, and the replacement of clover_exchange / clover_min /
+ * clover_sum (clover.f90:348-500, :3621-3709) by device-side pack + NCCL.
+ *
+ * Errors: the reference ABI has no status channel.  Any CUDA / NCCL failure prints a diagnostic
+ * to stderr and calls abort(); nothing here ever falls back to a CPU path.
+ */
+#ifndef CLOVER_B200_H
+#define CLOVER_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* Part 1: the reference's kernel entry points (file:line = the reference definition replaced) */
+
+/* kernels/ideal_gas_kernel_c.c:30   called from ideal_gas.f90:64,74 */
+void ideal_gas_kernel_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *density,
+                         double *energy, double *pressure, double *soundspeed);
+
+/* kernels/viscosity_kernel_c.c:31   called from viscosity.f90:57 */
+void viscosity_kernel_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *celldx, double *celldy,
+                         double *density0, double *pressure, double *viscosity, double *xvel0,
+                         double *yvel0);
+
+/* kernels/calc_dt_kernel_c.c:31     called from calc_dt.f90:83.  dt_min (work_array1) is scratch
+ * in the reference and is NOT written here; dtlcontrol=1, jldt=kldt=1 as in the reference. */
+void calc_dt_kernel_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *g_small, double *g_big,
+                       double *dtmin, double *dtc_safe, double *dtu_safe, double *dtv_safe,
+                       double *dtdiv_safe, double *xarea, double *yarea, double *cellx, double *celly,
+                       double *celldx, double *celldy, double *volume, double *density0,
+                       double *energy0, double *pressure, double *viscosity, double *soundspeed,
+                       double *xvel0, double *yvel0, double *dt_min, double *dt_min_val,
+                       int *dtl_control, double *xl_pos, double *yl_pos, int *jldt, int *kldt,
+                       int *small);
+
+/* kernels/PdV_kernel_c.c:32         called from PdV.f90:89.  *prdct==0 is the predictor.
+ * volume_change (work_array1) is scratch in the reference and is NOT written here. */
+void pdv_kernel_c_(int *prdct, int *xmin, int *xmax, int *ymin, int *ymax, double *dt, double *xarea,
+                   double *yarea, double *volume, double *density0, double *density1, double *energy0,
+                   double *energy1, double *pressure, double *viscosity, double *xvel0, double *xvel1,
+                   double *yvel0, double *yvel1, double *volume_change);
+
+/* kernels/revert_kernel_c.c:32      called from revert.f90:53 */
+void revert_kernel_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *density0, double *density1,
+                      double *energy0, double *energy1);
+
+/* kernels/accelerate_kernel_c.c:30  called from accelerate.f90:64 */
+void accelerate_kernel_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *dt, double *xarea,
+                          double *yarea, double *volume, double *density0, double *pressure,
+                          double *viscosity, double *xvel0, double *yvel0, double *xvel1,
+                          double *yvel1);
+
+/* kernels/flux_calc_kernel_c.c:29   called from flux_calc.f90:62 */
+void flux_calc_kernel_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *dt, double *xarea,
+                         double *yarea, double *xvel0, double *yvel0, double *xvel1, double *yvel1,
+                         double *vol_flux_x, double *vol_flux_y);
+
+/* kernels/advec_cell_kernel_c.c:30  called from advec_cell_driver.f90:59.  The seven work arrays
+ * are scratch in the reference; the device kernels keep those intermediates on chip and do NOT
+ * write them. */
+void advec_cell_kernel_c_(int *xmin, int *xmax, int *ymin, int *ymax, int *dir, int *sweep_number,
+                          double *vertexdx, double *vertexdy, double *volume, double *density1,
+                          double *energy1, double *mass_flux_x, double *vol_flux_x,
+                          double *mass_flux_y, double *vol_flux_y, double *pre_vol, double *post_vol,
+                          double *pre_mass, double *post_mass, double *advec_vol, double *post_ener,
+                          double *ener_flux);
+
+/* kernels/advec_mom_kernel_c.c:32   called from advec_mom_driver.f90:85,108.  Six scratch work
+ * arrays, NOT written (see advec_cell). */
+void advec_mom_kernel_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *vel1,
+                         double *mass_flux_x, double *vol_flux_x, double *mass_flux_y,
+                         double *vol_flux_y, double *volume, double *density1, double *node_flux,
+                         double *node_mass_post, double *node_mass_pre, double *mom_flux,
+                         double *pre_vol, double *post_vol, double *celldx, double *celldy,
+                         int *which_vel, int *sweep_number, int *direction);
+
+/* kernels/reset_field_kernel_c.c:30 called from reset_field.f90:63 */
+void reset_field_kernel_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *density0,
+                           double *density1, double *energy0, double *energy1, double *xvel0,
+                           double *xvel1, double *yvel0, double *yvel1);
+
+/* kernels/update_halo_kernel_c.c:32 called from update_halo.f90:86 */
+void update_halo_kernel_c_(int *xmin, int *xmax, int *ymin, int *ymax, int *chunk_neighbours,
+                           int *tile_neighbours, double *density0, double *energy0, double *pressure,
+                           double *viscosity, double *soundspeed, double *density1, double *energy1,
+                           double *xvel0, double *yvel0, double *xvel1, double *yvel1,
+                           double *vol_flux_x, double *vol_flux_y, double *mass_flux_x,
+                           double *mass_flux_y, int *fields, int *depth);
+
+/* kernels/field_summary_kernel_c.c:30 called from field_summary.f90:91 */
+void field_summary_kernel_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *volume,
+                             double *density0, double *energy0, double *pressure, double *xvel0,
+                             double *yvel0, double *vol, double *mass, double *ie, double *ke,
+                             double *press);
+
+/* kernels/pack_kernel_c.c:29,81,133,185,237,288,339,390  called from clover.f90:698-3605.
+ * `buffer` is the HOST communication buffer (clover.f90:329-342); its device mirror grows on
+ * demand.  These eight exist for drop-in completeness and A/B tests; the fast path is
+ * clover_b200_exchange_ below, which never touches host buffers. */
+void clover_pack_message_left_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *field,
+                                 double *buffer, int *cell_data, int *vertex_data, int *x_face_data,
+                                 int *y_face_data, int *depth, int *field_type, int *buffer_offset);
+void clover_unpack_message_left_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *field,
+                                   double *buffer, int *cell_data, int *vertex_data,
+                                   int *x_face_data, int *y_face_data, int *depth, int *field_type,
+                                   int *buffer_offset);
+void clover_pack_message_right_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *field,
+                                  double *buffer, int *cell_data, int *vertex_data, int *x_face_data,
+                                  int *y_face_data, int *depth, int *field_type, int *buffer_offset);
+void clover_unpack_message_right_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *field,
+                                    double *buffer, int *cell_data, int *vertex_data,
+                                    int *x_face_data, int *y_face_data, int *depth, int *field_type,
+                                    int *buffer_offset);
+void clover_pack_message_top_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *field,
+                                double *buffer, int *cell_data, int *vertex_data, int *x_face_data,
+                                int *y_face_data, int *depth, int *field_type, int *buffer_offset);
+void clover_unpack_message_top_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *field,
+                                  double *buffer, int *cell_data, int *vertex_data, int *x_face_data,
+                                  int *y_face_data, int *depth, int *field_type, int *buffer_offset);
+void clover_pack_message_bottom_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *field,
+                                   double *buffer, int *cell_data, int *vertex_data,
+                                   int *x_face_data, int *y_face_data, int *depth, int *field_type,
+                                   int *buffer_offset);
+void clover_unpack_message_bottom_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *field,
+                                     double *buffer, int *cell_data, int *vertex_data,
+                                     int *x_face_data, int *y_face_data, int *depth, int *field_type,
+                                     int *buffer_offset);
+
+/* kernels/initialise_chunk_kernel_c.c:29 called from initialise_chunk.f90:61 */
+void initialise_chunk_kernel_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *min_x,
+                                double *min_y, double *dx, double *dy, double *vertexx,
+                                double *vertexdx, double *vertexy, double *vertexdy, double *cellx,
+                                double *celldx, double *celly, double *celldy, double *volume,
+                                double *xarea, double *yarea);
+
+/* kernels/generate_chunk_kernel_c.c:33 called from generate_chunk.f90:77 */
+void generate_chunk_kernel_c_(int *xmin, int *xmax, int *ymin, int *ymax, double *vertexx,
+                              double *vertexy, double *cellx, double *celly, double *density0,
+                              double *energy0, double *xvel0, double *yvel0, int *number_of_states,
+                              double *state_density, double *state_energy, double *state_xvel,
+                              double *state_yvel, double *state_xmin, double *state_xmax,
+                              double *state_ymin, double *state_ymax, double *state_radius,
+                              int *state_geometry, int *g_rect, int *g_circ, int *g_point);
+
+/* timer_c.c:32  called from timer.f90:31 (host wall clock; kept so the library links in place
+ * of the reference's C objects) */
+void timer_c_(double *elapsed_time);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Part 2: GPU-backend extension (no reference counterpart unless cited) */
+
+/* Select the CUDA device and create the streams.  Optional: the first kernel call does it on
+ * device 0 (or $CLOVER_B200_DEVICE).  Aborts if no sm_100 device is present. */
+void clover_b200_init_(int *device);
+/* Free every device mirror, the streams and the communicator. */
+void clover_b200_finalize_(void);
+
+/* Residency.  *on != 0 (default): arrays are uploaded the first time their host address is seen
+ * and then live on the device; results stay there until clover_b200_sync_to_host_.  *on == 0:
+ * copy-in / copy-out -- every call uploads its inputs from the host arrays and downloads its
+ * outputs before returning (a literal drop-in, used by the per-kernel A/B tests and the
+ * host-buffer `e2e` measurement). */
+void clover_b200_set_resident_(int *on);
+/* Forget all device mirrors (the host arrays were modified behind the library's back). */
+void clover_b200_invalidate_(void);
+/* Forget the mirror of ONE host array (call before the host frees / re-uses that address). */
+void clover_b200_forget_(double *host_array);
+/* Re-upload one array from its host copy (same effect as invalidate for that array only). */
+void clover_b200_upload_(double *host_array);
+/* Copy one array (any host address the library has seen) back to the host. */
+void clover_b200_download_(double *host_array);
+/* Copy back the fields of the registered chunk selected by the 15-entry mask (ids of
+ * data.f90:51-66); this is the hook visit.f90 / a debugger needs. */
+void clover_b200_sync_to_host_(int *fields);
+/* Block until all device work issued so far has finished. */
+void clover_b200_device_synchronize_(void);
+
+/* Tell the library which host arrays are the 15 exchangeable fields of this process's chunk and
+ * who its neighbours are (chunk numbers, 1-based, -1 = external; order left,right,bottom,top as
+ * chunk%chunk_neighbours in definitions.f90:172-201).  Needed by exchange_ and sync_to_host_. */
+void clover_b200_register_chunk_(int *xmin, int *xmax, int *ymin, int *ymax, int *chunk_neighbours,
+                                 double *density0, double *density1, double *energy0,
+                                 double *energy1, double *pressure, double *viscosity,
+                                 double *soundspeed, double *xvel0, double *xvel1, double *yvel0,
+                                 double *yvel1, double *vol_flux_x, double *vol_flux_y,
+                                 double *mass_flux_x, double *mass_flux_y);
+
+/* Communicator bootstrap (replaces clover_init_comms, clover.f90:70-94).  Rank 0 calls
+ * get_unique_id_ (128 bytes), the host side broadcasts it by any means (MPI_BCAST in the Fortran
+ * driver, torch.distributed in bench.py), every rank calls comm_init_.  rank = chunk - 1. */
+void clover_b200_comm_get_unique_id_(char *id128);
+void clover_b200_comm_init_(int *nranks, int *rank, char *id128);
+
+/* clover_exchange (clover.f90:348-500): device pack of all requested fields per face ->
+ * ncclSend/ncclRecv with the face neighbours (left/right phase, then bottom/top phase so the
+ * corners propagate) -> device unpack.  Buffer layout inside a message is the reference's
+ * (per-field offset = running sum of depth*(edge+5), clover.f90:368-375). */
+void clover_b200_exchange_(int *fields, int *depth);
+/* clover_min (clover.f90:3640-3656): ncclAllReduce(min) of one double, result on every rank. */
+void clover_b200_min_(double *value);
+/* clover_sum (clover.f90:3621-3637), n values at once: ncclAllReduce(sum); result on every rank
+ * (the reference reduces to rank 0 only). */
+void clover_b200_sum_(double *values, int *n);
+
+/* Accounting for bench.py: kernels launched so far by this library, and (when enabled with
+ * *on != 0) per-kernel CUDA-event timing accumulated by name. */
+void clover_b200_launch_count_(long long *n);
+void clover_b200_profile_(int *on);
+/* Writes up to *max entries; names are 32-byte NUL-padded records; returns the number in *n. */
+void clover_b200_profile_get_(int *max, char *names32, double *total_ms, long long *calls, int *n);
+void clover_b200_profile_reset_(void);
+/* Bytes copied host->device and device->host so far (all modes). */
+void clover_b200_copy_bytes_(long long *h2d, long long *d2h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLOVER_B200_H */
