@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- cell-updates/s and ms/step of the CloverLeaf hydro step on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--deck NAME]
+
+Workload: clover_bm16_short (3840^2 cells, the configuration BASELINE.json's metric is quoted on).  A
+"step" is one trip of the reference's hydro loop (hydro.f90:48-99: timestep, PdV x2, accelerate,
+flux_calc, advection, reset_field, + field_summary every 10th step), driven by the C++ restatement
+of the Fortran driver through the reference's `*_kernel_c_` C-ABI.
+
+N > 1 (torchrun, one rank per GPU): the same mesh is decomposed by clover_decompose into N chunks,
+one per GPU (strong scaling); halos travel device->device over NCCL, dt by ncclAllReduce(min).
+
+Printed JSON (one line, rank 0): see the contract in the task statement.  Extra keys:
+  value        device-timed (CUDA events on the library's stream), state resident in HBM
+  e2e          same metric through the same C-ABI but starting from HOST arrays: upload of the whole
+               host-resident state (pinned) + K steps (8-byte dt readback each) + final summary +
+               download of the four state fields, all inside the timed region
+  roofline     dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events)
+  step_roofline  whole step: 856 B x cells / ms_per_step against the same peak
+  cpu_baseline the reference's own C kernels (oracle/_ref, OpenMP, all host cores) on a bounded sample
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_CELL_STEP = 856.0  # 107 fp64 array passes
+# algorithmic array passes per launch (SURVEY.md section 8a "alg" column; advec_mom: half of the fused
+# two-component figure per single-component call)
+KERNEL_PASSES = {
+    "ideal_gas": 4, "viscosity": 5, "calc_dt": 8, "pdv_predict": 11, "pdv_correct": 13, "revert": 4,
+    "accelerate": 10, "flux_calc": 8, "advec_cell_x": 7.5, "advec_cell_y": 7.5, "advec_mom_x": 4.25,
+    "advec_mom_y": 4.25, "reset_field": 8, "field_summary": 6,
+}
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_copy_gbs", "hbm_gb_s"):
+                if k in j:
+                    return float(j[k]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def big_deck(name):
+    """The deck with the stop criteria pushed out so that warm-up + timed steps always fit."""
+    from cloverleaf_b200.driver import deck_text
+    out = []
+    for line in deck_text(name).splitlines():
+        s = line.strip()
+        if s.startswith("end_time") or s.startswith("end_step") or s.startswith("test_problem"):
+            continue
+        if s.startswith("*endclover"):
+            out += [" end_time=1000.0", " end_step=1000000"]
+        out.append(line)
+    return "\n".join(out) + "\n"
+
+
+def cells_of(deck):
+    nx = ny = None
+    for tok in deck.replace("=", " ").split("\n"):
+        w = tok.split()
+        if len(w) >= 2 and w[0] == "x_cells":
+            nx = int(w[1])
+        if len(w) >= 2 and w[0] == "y_cells":
+            ny = int(w[1])
+    return nx, ny
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_run(deck, steps, warmup, budget_s=150.0):
+    """The reference's C kernels (oracle/_ref, else the oracle port) on all host cores.  If the full
+    mesh would blow the time budget the sample is a smaller mesh of the same deck (cell-updates/s is
+    the unit, so the sample scales)."""
+    from cloverleaf_b200.driver import Driver
+    ref = os.path.join(ROOT, "oracle", "_ref", "libclover_ref_c_fast.so")
+    kind = "reference"
+    if not os.path.exists(ref):
+        ref = os.path.join(ROOT, "oracle", "libclover_oracle.so")
+        kind = "port"
+        if not os.path.exists(ref):
+            from cloverleaf_b200 import build
+            build.build_oracle()
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ.setdefault("OMP_PROC_BIND", "true")
+    nx, ny = cells_of(deck)
+    shrink = 1
+    while True:
+        d_text = deck.replace("x_cells=%d" % nx, "x_cells=%d" % (nx // shrink)).replace(
+            "y_cells=%d" % ny, "y_cells=%d" % (ny // shrink))
+        d = Driver(d_text, ref)
+        d.start()
+        t0 = time.perf_counter()
+        d.run(1)
+        t1 = time.perf_counter() - t0
+        if t1 * (steps + warmup) <= budget_s or nx // (shrink * 2) < 240:
+            break
+        d.close()
+        shrink *= 2
+    if warmup > 1:
+        d.run(warmup - 1)
+    t0 = time.perf_counter()
+    done = d.run(steps)
+    wall = time.perf_counter() - t0
+    cells = (nx // shrink) * (ny // shrink)
+    d.close()
+    return dict(value=cells * done / wall, ms_per_step=1e3 * wall / done, cores=cores, kind=kind, steps=done,
+                sample="%dx%d cells (%s of the %dx%d workload), %d timed steps, %s, OMP_NUM_THREADS=%d" % (
+                    nx // shrink, ny // shrink, "all" if shrink == 1 else "1/%d" % (shrink * shrink), nx, ny, done,
+                    os.path.basename(ref), cores))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--deck", default="clover_bm16_short.in")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    deck = big_deck(args.deck)
+    nx, ny = cells_of(deck)
+    workload = "%s %dx%d" % (args.deck.replace(".in", ""), nx, ny)
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(deck, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": "cell-updates/s", "value": r["value"], "unit": "cell-updates/s",
+                "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic (deck-defined initial state, no RNG)",
+                "config": {"workload": workload, "note": "reference C kernels (use_c_kernels path) + OpenMP on host cores"},
+                "cpu_baseline": {"value": r["value"], "unit": "cell-updates/s", "cores": r["cores"],
+                                 "kind": r["kind"], "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm (CUDA)
+    import cloverleaf_b200
+    from cloverleaf_b200.driver import Driver
+    lib = cloverleaf_b200.load_b200()  # raises if missing: no CPU fallback
+    ci, cd, cll = ctypes.c_int, ctypes.c_double, ctypes.c_longlong
+    dev = ci(local_rank)
+    lib.clover_b200_init_(ctypes.byref(dev))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idbuf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            lib.clover_b200_comm_get_unique_id_(idbuf)
+        t = torch.tensor(list(idbuf.raw), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        idbuf = ctypes.create_string_buffer(bytes(t.cpu().tolist()), 128)
+        nr, rk = ci(world), ci(rank)
+        lib.clover_b200_comm_init_(ctypes.byref(nr), ctypes.byref(rk), idbuf)
+
+    def barrier():
+        lib.clover_b200_device_synchronize_()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def launches():
+        n = cll(0)
+        lib.clover_b200_launch_count_(ctypes.byref(n))
+        return n.value
+
+    def copied():
+        a, b = cll(0), cll(0)
+        lib.clover_b200_copy_bytes_(ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
+    def timed_steps(d, k):
+        """K hydro steps bracketed by barrier+sync, timed with CUDA events on the library's stream."""
+        s0, s1, ms = ci(0), ci(1), cd(0)
+        barrier()
+        lib.clover_b200_event_record_(ctypes.byref(s0))
+        t0 = time.perf_counter()
+        done = d.run(k)
+        lib.clover_b200_event_record_(ctypes.byref(s1))
+        lib.clover_b200_event_elapsed_ms_(ctypes.byref(s0), ctypes.byref(s1), ctypes.byref(ms))
+        barrier()
+        wall = time.perf_counter() - t0
+        return done, ms.value, wall
+
+    comm_mode = 1 if world > 1 else 0
+    d = Driver(deck, cloverleaf_b200.LIB_B200, nchunks=world, rank=rank, comm_mode=comm_mode)
+    d.start()
+    d.run(args.warmup)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = launches()
+    done, ms, wall = timed_steps(d, args.steps)
+    l1 = launches()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms)
+    cells = nx * ny
+    value = cells * done / (ms * 1e-3)
+    ms_per_step = ms / done
+
+    # ---- per-kernel launch durations (CUDA events around every launch; outside the timed region)
+    prof = {}
+    if args.profile_steps > 0:
+        on, off = ci(1), ci(0)
+        lib.clover_b200_profile_reset_()
+        lib.clover_b200_profile_(ctypes.byref(on))
+        d.run(args.profile_steps)
+        lib.clover_b200_profile_(ctypes.byref(off))
+        mx = ci(64); n = ci(0)
+        names = ctypes.create_string_buffer(32 * 64)
+        tot = (cd * 64)(); calls = (cll * 64)()
+        lib.clover_b200_profile_get_(ctypes.byref(mx), names, tot, calls, ctypes.byref(n))
+        for i in range(n.value):
+            nm = names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode()
+            prof[nm] = dict(ms_total=tot[i], calls=calls[i], ms_avg=tot[i] / max(calls[i], 1))
+    chunk_cells = d.chunk_info(0)["x_max"] * d.chunk_info(0)["y_max"]
+    peak, peak_src = hbm_peak()
+    roofline = None
+    kernels = {}
+    if prof:
+        step_ms = sum(p["ms_total"] for p in prof.values()) / args.profile_steps
+        for nm, p in sorted(prof.items(), key=lambda kv: -kv[1]["ms_total"]):
+            passes = KERNEL_PASSES.get(nm)
+            gbs = passes * 8.0 * chunk_cells / (p["ms_avg"] * 1e-3) / 1e9 if passes else None
+            kernels[nm] = dict(ms_avg=round(p["ms_avg"], 5), calls_per_step=p["calls"] / args.profile_steps,
+                               share=round(p["ms_total"] / args.profile_steps / step_ms, 4),
+                               alg_gbs=round(gbs, 1) if gbs else None,
+                               frac=round(gbs / peak, 4) if gbs else None)
+        top = next(nm for nm in kernels if KERNEL_PASSES.get(nm))
+        roofline = {"kernel": top, "bound": "hbm", "achieved": kernels[top]["alg_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kernels[top]["frac"], "traffic": None, "peak_source": peak_src,
+                    "alg_bytes_per_launch": KERNEL_PASSES[top] * 8.0 * chunk_cells,
+                    "ms_per_launch": kernels[top]["ms_avg"]}
+    step_gbs = ALG_BYTES_PER_CELL_STEP * cells / world / (ms_per_step * 1e-3) / 1e9
+    chunks = "%dx%d (clover_decompose)" % (d.grid()["chunk_x"], d.grid()["chunk_y"])
+    d.close()
+
+    # ---- end to end from host arrays (same C-ABI, resident mode, copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        d2 = Driver(deck, cloverleaf_b200.LIB_B200, nchunks=world, rank=rank, comm_mode=comm_mode)
+        d2.start()
+        d2.run(args.warmup)
+        # bring the whole state back to the (pinned) host arrays and drop the device copies: the state
+        # now lives in host memory only, as it would after the Fortran driver's own initialisation
+        names2d = ["density0", "density1", "energy0", "energy1", "pressure", "viscosity", "soundspeed", "xvel0",
+                   "xvel1", "yvel0", "yvel1", "vol_flux_x", "vol_flux_y", "mass_flux_x", "mass_flux_y", "volume",
+                   "xarea", "yarea"]
+        names1d = ["cellx", "celly", "celldx", "celldy", "vertexx", "vertexy", "vertexdx", "vertexdy"]
+        info = d2.chunk_info(0)
+        cnx, cny = info["x_max"], info["y_max"]
+        ptrs = {}
+        for nm in names2d + names1d:
+            p = d2._L.clover_driver_field(d2._h, 0, nm.encode())
+            ptrs[nm] = p
+            nbytes = cll(8 * (cnx + 5) * (cny + 5) if nm in names2d else 8 * (max(cnx, cny) + 5))
+            lib.clover_b200_download_(ctypes.c_void_p(p))
+        lib.clover_b200_device_synchronize_()
+        for nm in names2d:
+            from cloverleaf_b200.driver import FIELD_SHAPES
+            ex, ey = FIELD_SHAPES[nm]
+            nbytes = cll(8 * (cnx + 4 + ex) * (cny + 4 + ey))
+            lib.clover_b200_pin_(ctypes.c_void_p(ptrs[nm]), ctypes.byref(nbytes))
+        for nm in names2d + names1d:
+            lib.clover_b200_forget_(ctypes.c_void_p(ptrs[nm]))
+        h0, g0 = copied()
+        barrier()
+        t0 = time.perf_counter()
+        done2 = d2.run(args.steps)
+        for nm in ("density0", "energy0", "xvel0", "yvel0"):
+            lib.clover_b200_download_(ctypes.c_void_p(ptrs[nm]))
+        barrier()
+        wall2 = max_over_ranks(time.perf_counter() - t0)
+        h1, g1 = copied()
+        e2e = {"value": cells * done2 / wall2, "unit": "cell-updates/s", "ms_per_step": 1e3 * wall2 / done2,
+               "h2d_bytes_per_step": (h1 - h0) / done2, "d2h_bytes_per_step": (g1 - g0) / done2,
+               "note": "host-resident state (pinned) -> upload on first use + %d steps + download of the 4 state "
+                       "fields; wall clock, max over ranks" % done2}
+        for nm in names2d:
+            lib.clover_b200_unpin_(ctypes.c_void_p(ptrs[nm]))
+        d2.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(deck, 6, 1, budget_s=25.0)
+        cpu = {"value": r["value"], "unit": "cell-updates/s", "cores": r["cores"], "kind": r["kind"],
+               "sample": r["sample"], "ms_per_step": r["ms_per_step"]}
+
+    if rank == 0:
+        line = {
+            "metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": done,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic (deck-defined initial state, no RNG)",
+            "config": {"workload": workload, "chunks": chunks,
+                       "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (25 * 8 * chunk_cells / 1e9),
+                       "timing": "CUDA events on the library stream, max over ranks; host wall %.3f s" % wall},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": l1 - l0,
+            "roofline": roofline,
+            "step_roofline": {"bound": "hbm", "alg_bytes_per_cell_step": ALG_BYTES_PER_CELL_STEP,
+                              "achieved": round(step_gbs, 1), "peak": peak, "unit": "GB/s",
+                              "frac": round(step_gbs / peak, 4), "frac_of_8TBs_nominal": round(step_gbs / 8000.0, 4),
+                              "peak_source": peak_src},
+            "kernels": kernels, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

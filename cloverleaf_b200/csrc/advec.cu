@@ -44,12 +44,12 @@ __device__ __forceinline__ void cell_face_flux(double vf, double pre_vol_donor, 
                                                double d_down, double e_up, double e_don, double e_down,
                                                double vd_face, double vd_dif, double& mass_flux,
                                                double& ener_flux) {
-  const double sigmat = fabs(vf / pre_vol_donor);
+  const double sigmat = fabs(ddiv(vf, pre_vol_donor));
   const double sigma3 = (1.0 + sigmat) * (vd_face / vd_dif);
   const double sigma4 = 2.0 - sigmat;
   double limiter = cell_limiter(1.0 - sigmat, d_don - d_up, d_down - d_don, sigma3, sigma4);
   mass_flux = vf * (d_don + limiter);
-  const double sigmam = fabs(mass_flux) / (d_don * pre_vol_donor);
+  const double sigmam = ddiv(fabs(mass_flux), d_don * pre_vol_donor);
   limiter = cell_limiter(1.0 - sigmam, e_don - e_up, e_down - e_don, sigma3, sigma4);
   ener_flux = mass_flux * (e_don + limiter);
 }
@@ -58,7 +58,7 @@ __device__ __forceinline__ void cell_face_flux(double vf, double pre_vol_donor, 
 __device__ __forceinline__ double mom_face_flux(double nf, double node_mass_pre_donor, double v_up,
                                                 double v_don, double v_down, double width,
                                                 double width_dif) {
-  const double sigma = fabs(nf) / node_mass_pre_donor;
+  const double sigma = ddiv(fabs(nf), node_mass_pre_donor);
   const double vdiffuw = v_don - v_up;
   const double vdiffdw = v_down - v_don;
   double limiter = 0.0;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(32 * AMX_ROWS)
     if (owned) {
       const size_t o = idx2(pitch, j, k);
       if (j >= 1 && j <= nx + 1)
-        vnew[v][o] = (vel[o] * nm_pre + mom_flux_left - mom_flux) / nm_post;  // :191-201
+        vnew[v][o] = ddiv(vel[o] * nm_pre + mom_flux_left - mom_flux, nm_post);  // :191-201
       else
         vnew[v][o] = vel[o];
     }
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(AMY_THREADS)
       const double vp2 = vold[v][c + 2 * P];
       const double mom = mom_face_flux(nf0, nmp_don, neg ? vp2 : vm1[v], neg ? vp1[v] : v0[v],
                                        neg ? v0[v] : vp1[v], width, width_dif);
-      if (k >= ks) vnew[v][c] = (v0[v] * nmpre0 + mom_prev[v] - mom) / nmpost0;  // :272-282
+      if (k >= ks) vnew[v][c] = ddiv(v0[v] * nmpre0 + mom_prev[v] - mom, nmpost0);  // :272-282
       mom_prev[v] = mom;
       vm1[v] = v0[v]; v0[v] = vp1[v]; vp1[v] = vp2;
     }

@@ -70,13 +70,13 @@ __global__ void __launch_bounds__(BX* BY)
   const double ugrad = (u10 + u11) - (u00 + u01);
   const double vgrad = (v01 + v11) - (v00 + v10);
   const double div = dx * ugrad + dy * vgrad;
-  const double strain2 = 0.5 * (u01 + u11 - u00 - u10) / dy + 0.5 * (v10 + v11 - v00 - v01) / dx;
-  double pgradx = (pressure[c + 1] - pressure[c - 1]) / (dx + celldx[j + 2]);
-  double pgrady = (pressure[c + pitch] - pressure[c - pitch]) / (dy + celldy[k + 2]);
+  const double strain2 = ddiv(0.5 * (u01 + u11 - u00 - u10), dy) + ddiv(0.5 * (v10 + v11 - v00 - v01), dx);
+  double pgradx = ddiv(pressure[c + 1] - pressure[c - 1], dx + celldx[j + 2]);
+  double pgrady = ddiv(pressure[c + pitch] - pressure[c - pitch], dy + celldy[k + 2]);
   const double pgradx2 = pgradx * pgradx, pgrady2 = pgrady * pgrady;
   const double limiter =
-      ((0.5 * ugrad / dx) * pgradx2 + (0.5 * vgrad / dy) * pgrady2 + strain2 * pgradx * pgrady) /
-      dmax(pgradx2 + pgrady2, 1.0e-16);
+      ddiv(ddiv(0.5 * ugrad, dx) * pgradx2 + ddiv(0.5 * vgrad, dy) * pgrady2 + strain2 * pgradx * pgrady,
+           dmax(pgradx2 + pgrady2, 1.0e-16));
   double q = 0.0;
   if (!(limiter > 0.0 || div >= 0.0)) {
     const double ax = dmax(1.0e-16, fabs(pgradx)), ay = dmax(1.0e-16, fabs(pgrady));
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(BX* BY)
     const double dsx = celldx[j + 1], dsy = celldy[k + 1];
     const double vol = volume[c];
     double cc = soundspeed[c] * soundspeed[c];
-    cc = cc + 2.0 * viscosity[c] / density0[c];
+    cc = cc + ddiv(2.0 * viscosity[c], density0[c]);
     cc = dmax(sqrt(cc), P.g_small);
     const double dtct = P.dtc_safe * dmin(dsx, dsy) / cc;
     double div = 0.0;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(BX* BY)
     dv2 = (yvel0[c + pitch] + yvel0[c + pitch + 1]) * yarea[c + pitch];
     div = div + dv2 - dv1;
     const double dtvt = P.dtv_safe * 2.0 * vol / dmax(fabs(dv1), dmax(fabs(dv2), P.g_small * vol));
-    div = div / (2.0 * vol);
+    div = ddiv(div, 2.0 * vol);
     const double dtdivt = (div < -P.g_small) ? P.dtdiv_safe * (-1.0 / div) : P.g_big;
     m[0] = dmin(dtct, dmin(dtut, dmin(dtvt, dtdivt)));
   }
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(BX* BY)
   const double vc = vol / (vol + total);
   const double recip = 1.0 / vol;
   const double rho0 = density0[c];
-  const double de = (pressure[c] / rho0 + viscosity[c] / rho0) * total * recip;
+  const double de = (pressure[c] / rho0 + ddiv(viscosity[c], rho0)) * total * recip;
   energy1[c] = energy0[c] - de;
   density1[c] = rho0 * vc;
 }

@@ -439,3 +439,36 @@ void timer_c_(double* elapsed_time) {
 }
 
 }  // extern "C"
+
+// ---- device-side timing and host pinning for bench.py ---------------------------------------------
+namespace {
+cudaEvent_t g_events[8] = {};
+}
+extern "C" {
+// Record event `slot` (0..7) on the library's stream.
+void clover_b200_event_record_(int* slot) {
+  clv::ensure_init();
+  if (*slot < 0 || *slot >= 8) clv::fatal("event slot %d", *slot);
+  if (!g_events[*slot]) CLV_CUDA(cudaEventCreate(&g_events[*slot]));
+  CLV_CUDA(cudaEventRecord(g_events[*slot], clv::stream()));
+}
+// Milliseconds between two recorded events (waits for the later one).
+void clover_b200_event_elapsed_ms_(int* a, int* b, double* ms) {
+  CLV_CUDA(cudaEventSynchronize(g_events[*b]));
+  float f = 0;
+  CLV_CUDA(cudaEventElapsedTime(&f, g_events[*a], g_events[*b]));
+  *ms = f;
+}
+// Page-lock a host array so that uploads/downloads run at full PCIe rate (optional).
+void clover_b200_pin_(double* host, long long* bytes) {
+  clv::ensure_init();
+  cudaError_t e = cudaHostRegister(host, (size_t)*bytes, cudaHostRegisterDefault);
+  if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered)
+    clv::fatal("cudaHostRegister(%lld bytes): %s", *bytes, cudaGetErrorString(e));
+  (void)cudaGetLastError();
+}
+void clover_b200_unpin_(double* host) {
+  (void)cudaHostUnregister(host);
+  (void)cudaGetLastError();
+}
+}

@@ -225,6 +225,14 @@ void clover_b200_profile_reset_(void);
 /* Bytes copied host->device and device->host so far (all modes). */
 void clover_b200_copy_bytes_(long long *h2d, long long *d2h);
 
+/* Device-side timing for bench.py: record event `slot` (0..7) on the library's stream; elapsed
+ * milliseconds between two recorded slots (waits for the later one). */
+void clover_b200_event_record_(int *slot);
+void clover_b200_event_elapsed_ms_(int *slot_a, int *slot_b, double *ms);
+/* Page-lock / unlock a host array (optional; uploads and downloads then run at full PCIe rate). */
+void clover_b200_pin_(double *host_array, long long *bytes);
+void clover_b200_unpin_(double *host_array);
+
 #ifdef __cplusplus
 }
 #endif

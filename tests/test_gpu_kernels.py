@@ -3,7 +3,8 @@ arrays (copy-in / copy-out mode), against the oracle on the same seeded inputs.
 
 Bar: BIT-EXACT for every field a kernel writes (the library is built -fmad=false and keeps the
 reference's evaluation order).  Only the sum reductions of field_summary are compared with a
-tolerance (1e-13 relative: fixed-tree device sum vs serial CPU sum); the calc_dt minimum is exact.
+tolerance (1e-11 relative, 10x inside the north_star's 1e-10: the device sum is a fixed tree, the CPU
+sum is serial and carries ~n*eps of its own rounding); the calc_dt minimum is exact.
 Work arrays are scratch in the reference and are not written by the device kernels, so they are
 excluded from the comparison.
 """
@@ -54,7 +55,7 @@ def test_kernel_matches_oracle(cuda, oracle_lib, case, nx, ny):
         assert ob["dtl_control"] == 1 and ob["jldt"] == 1 and ob["kldt"] == 1
     if name == "field_summary":
         for k in ("vol", "mass", "ie", "ke", "press"):
-            assert abs(oa[k] - ob[k]) <= 1e-13 * abs(oa[k]), (k, oa[k], ob[k])
+            assert abs(oa[k] - ob[k]) <= 1e-11 * abs(oa[k]), (k, oa[k], ob[k])
 
 
 @pytest.mark.parametrize("case", kc.halo_cases(), ids=lambda c: c[0])

@@ -21,7 +21,10 @@ from conftest import GOLDEN, ORACLE_PORT
 
 pytestmark = pytest.mark.gpu
 
-SUM_TOL = 1e-12
+# The north_star's bar.  The golden sums come from a SERIAL CPU accumulation that itself carries
+# ~1e-11 relative rounding at 960^2 (the committed volume reads 99.99999999880 for an exact 100);
+# the device tree sum is the more accurate of the two (100.00000000000003).
+SUM_TOL = 1e-10
 
 
 def _check_against(G_dt, G_sum, d, tol=SUM_TOL):
@@ -110,4 +113,4 @@ def test_bm16_short_first_steps_and_conservation(fresh):
         ref10 = [r for r in G["summaries"] if r["step"] <= 10]
         for a, b in zip(s, ref10):
             for k in ("volume", "mass", "pressure", "ie", "ke", "total"):
-                assert abs(a[k] - b[k]) <= 1e-11 * max(abs(b[k]), 1e-300), (k, a[k], b[k])
+                assert abs(a[k] - b[k]) <= SUM_TOL * max(abs(b[k]), 1e-300), (k, a[k], b[k])
