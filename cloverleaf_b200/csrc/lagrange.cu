@@ -7,15 +7,22 @@
 // with -ffp-contract=off.  Reductions: min is order-independent; sums use a fixed tree
 // (deterministic for a given mesh, differs from a serial CPU sum in the last bits only).
 //
-// Mapping: one thread per cell / vertex, threadIdx.x along j (unit stride, 128-byte aligned rows,
-// see common.cuh), 32x8 thread tiles; stencil neighbours come through L1.  All kernels here are
-// HBM-bound streaming passes; the algorithmic bytes per cell are listed in DESIGN.md.
+// Mapping: threadIdx.x along j (unit stride, 128-byte aligned rows, see common.cuh), 32x8 thread
+// tiles, and every thread handles NR rows (k, k+8, ...) in a fully unrolled loop whose loads are
+// unconditional (indices clamped into the loop range, only the stores are predicated).  That puts
+// NR independent load batches and NR independent fp64 dependency chains (the div/sqrt sequences are
+// ~10 dependent DFMAs each) in flight per thread: first profiles (profiles/r01b_full_ddiv.txt) showed
+// these kernels neither DRAM- nor issue-bound but latency-bound with one cell per thread.
+// Stencil neighbours come through L1.  Algorithmic bytes per cell are listed in DESIGN.md.
 #include "clover_b200.h"
 #include "common.cuh"
 
 namespace clv {
 
 constexpr int BX = 32, BY = 8;
+// rows per thread, per kernel (tuned on B200, see profiles/)
+constexpr int NR_IDEAL = 4, NR_VISC = 1, NR_DT = 1, NR_PDV = 2, NR_COPY = 4, NR_RESET = 1, NR_ACC = 1, NR_FLUX = 2,
+              NR_SUM = 2;
 
 struct Range {
   int j0, j1, k0, k1;  // inclusive
@@ -27,69 +34,153 @@ static inline Range make_range(int j0, int j1, int k0, int k1) {
   r.jbase = ((j0 + XOFF) & ~15) - XOFF;
   return r;
 }
-static inline dim3 grid_for(const Range& r) {
-  return dim3((unsigned)((r.j1 - r.jbase + 1 + BX - 1) / BX), (unsigned)((r.k1 - r.k0 + 1 + BY - 1) / BY), 1);
+static inline dim3 grid_for(const Range& r, int nr) {
+  return dim3((unsigned)((r.j1 - r.jbase + 1 + BX - 1) / BX),
+              (unsigned)((r.k1 - r.k0 + 1 + BY * nr - 1) / (BY * nr)), 1);
 }
-#define CLV_THREAD_JK(r)                                                  \
-  const int j = (r).jbase + (int)(blockIdx.x * BX + threadIdx.x);         \
-  const int k = (r).k0 + (int)(blockIdx.y * BY + threadIdx.y);            \
-  const bool active = (j >= (r).j0) && (j <= (r).j1) && (k <= (r).k1)
+// Opens the unrolled row loop: defines j, k (clamped into the range, always safe to load from) and
+// `active` (this thread really owns (j,k): predicate for stores / reductions).
+#define CLV_ROWS_BEGIN(r, NR)                                                          \
+  const int j_raw_ = (r).jbase + (int)(blockIdx.x * BX + threadIdx.x);                 \
+  const bool j_ok_ = (j_raw_ >= (r).j0) && (j_raw_ <= (r).j1);                         \
+  const int j = j_raw_ < (r).j0 ? (r).j0 : (j_raw_ > (r).j1 ? (r).j1 : j_raw_);        \
+  _Pragma("unroll") for (int rr_ = 0; rr_ < (NR); ++rr_) {                             \
+    const int k_raw_ = (r).k0 + (int)((blockIdx.y * (NR) + rr_) * BY + threadIdx.y);   \
+    const bool active = j_ok_ && (k_raw_ <= (r).k1);                                   \
+    const int k = k_raw_ <= (r).k1 ? k_raw_ : (r).k1;
+#define CLV_ROWS_END }
+// Persistent variant for the reduction kernels: a 1-D grid of a few CTAs per SM walks the same 32x(8*NR)
+// tiles in a grid-stride loop, so that the block-level reduction tail (fence + ticket atomic) is paid once
+// per CTA instead of once per tile (it held every warp of a 256-cell block hostage for ~2k cycles).
+#define CLV_PTILES_BEGIN(r, NR)                                                        \
+  const unsigned tiles_x_ = (unsigned)(((r).j1 - (r).jbase + BX) / BX);                \
+  const unsigned tiles_y_ = (unsigned)(((r).k1 - (r).k0 + BY * (NR)) / (BY * (NR)));   \
+  for (unsigned tile_ = blockIdx.x; tile_ < tiles_x_ * tiles_y_; tile_ += gridDim.x) { \
+    const unsigned bx_ = tile_ % tiles_x_, by_ = tile_ / tiles_x_;                     \
+    const int j_raw_ = (r).jbase + (int)(bx_ * BX + threadIdx.x);                      \
+    const bool j_ok_ = (j_raw_ >= (r).j0) && (j_raw_ <= (r).j1);                       \
+    const int j = j_raw_ < (r).j0 ? (r).j0 : (j_raw_ > (r).j1 ? (r).j1 : j_raw_);      \
+    _Pragma("unroll") for (int rr_ = 0; rr_ < (NR); ++rr_) {                           \
+      const int k_raw_ = (r).k0 + (int)((by_ * (NR) + rr_) * BY + threadIdx.y);        \
+      const bool active = j_ok_ && (k_raw_ <= (r).k1);                                 \
+      const int k = k_raw_ <= (r).k1 ? k_raw_ : (r).k1;
+#define CLV_PTILES_END }}
+static inline dim3 persistent_grid(const Range& r, int nr, int ctas_per_sm) {
+  const dim3 g = grid_for(r, nr);
+  const unsigned tiles = g.x * g.y, cap = 148u * (unsigned)ctas_per_sm;
+  return dim3(tiles < cap ? tiles : cap, 1, 1);
+}
 
 // ------------------------------------------------------------------------------------------------
 // ideal_gas_kernel_c.c:48-59.  4 passes (2 reads, 2 writes) = 32 B/cell.
+template <bool SAFE>
+__device__ __forceinline__ void ideal_gas_cell(double rho, double e, double& p, double& ss, bool& bad) {
+  const double v = Math<SAFE>::rcp(rho, bad);
+  p = (1.4 - 1.0) * rho * e;
+  const double pe = (1.4 - 1.0) * rho;
+  const double pv = -rho * p;
+  const double ss2 = v * v * (p * pe - pv);
+  ss = Math<SAFE>::sqrt(ss2, bad);
+}
+template <int NR>
 __global__ void __launch_bounds__(BX* BY)
     ideal_gas_kernel(Range r, int pitch, const double* __restrict__ density,
                      const double* __restrict__ energy, double* __restrict__ pressure,
                      double* __restrict__ soundspeed) {
-  CLV_THREAD_JK(r);
-  if (!active) return;
-  const size_t c = idx2(pitch, j, k);
-  const double rho = density[c];
-  const double v = 1.0 / rho;
-  const double p = (1.4 - 1.0) * rho * energy[c];
-  const double pe = (1.4 - 1.0) * rho;
-  const double pv = -rho * p;
-  const double ss2 = v * v * (p * pe - pv);
-  pressure[c] = p;
-  soundspeed[c] = sqrt(ss2);
+  double rho[NR], en[NR];
+  CLV_ROWS_BEGIN(r, NR)  // all loads first
+    const size_t c = idx2(pitch, j, k);
+    rho[rr_] = density[c];
+    en[rr_] = energy[c];
+    (void)active;
+  CLV_ROWS_END
+  double p[NR], ss[NR];
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < NR; ++i) ideal_gas_cell<false>(rho[i], en[i], p[i], ss[i], bad);
+  if (bad) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) ideal_gas_cell<true>(rho[i], en[i], p[i], ss[i], bad);
+  }
+  {
+    CLV_ROWS_BEGIN(r, NR)
+      if (active) {
+        const size_t c = idx2(pitch, j, k);
+        pressure[c] = p[rr_];
+        soundspeed[c] = ss[rr_];
+      }
+    CLV_ROWS_END
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // viscosity_kernel_c.c:53-104.  5 passes = 40 B/cell.
+struct ViscIn {
+  double u00, u10, u01, u11, v00, v10, v01, v11, dx, dy, dx1, dy1, pl, pr, pb, pt, rho;
+};
+template <bool SAFE>
+__device__ __forceinline__ double viscosity_cell(const ViscIn& I, bool& bad) {
+  typedef Math<SAFE> M;
+  const double ugrad = (I.u10 + I.u11) - (I.u00 + I.u01);
+  const double vgrad = (I.v01 + I.v11) - (I.v00 + I.v10);
+  const double div = I.dx * ugrad + I.dy * vgrad;
+  // viscosity_kernel_c.c:88: `if (limiter>0.0 || div>=0.0) viscosity = 0`.  The limiter (7 divisions)
+  // only decides anything for a compressing cell, so it is evaluated only there; everywhere else --
+  // the whole quiescent part of the mesh -- the answer is 0 whatever the limiter is.
+  if (div >= 0.0) return 0.0;
+  const double strain2 = M::div(0.5 * (I.u01 + I.u11 - I.u00 - I.u10), I.dy, bad) +
+                         M::div(0.5 * (I.v10 + I.v11 - I.v00 - I.v01), I.dx, bad);
+  double pgradx = M::div(I.pr - I.pl, I.dx + I.dx1, bad);
+  double pgrady = M::div(I.pt - I.pb, I.dy + I.dy1, bad);
+  const double pgradx2 = pgradx * pgradx, pgrady2 = pgrady * pgrady;
+  const double limiter = M::div(M::div(0.5 * ugrad, I.dx, bad) * pgradx2 + M::div(0.5 * vgrad, I.dy, bad) * pgrady2 +
+                                    strain2 * pgradx * pgrady,
+                                dmax(pgradx2 + pgrady2, 1.0e-16), bad);
+  double q = 0.0;
+  if (!(limiter > 0.0)) {  // generic operators in this minority branch
+    const double ax = dmax(1.0e-16, fabs(pgradx)), ay = dmax(1.0e-16, fabs(pgrady));
+    pgradx = (pgradx < 0.0) ? -ax : ax;
+    pgrady = (pgrady < 0.0) ? -ay : ay;
+    const double pgrad = sqrt(pgradx * pgradx + pgrady * pgrady);
+    const double xgrad = fabs(I.dx * pgrad / pgradx);
+    const double ygrad = fabs(I.dy * pgrad / pgrady);
+    const double grad = dmin(xgrad, ygrad);
+    const double grad2 = grad * grad;
+    q = 2.0 * I.rho * grad2 * limiter * limiter;
+  }
+  return q;
+}
+
+template <int NR>
 __global__ void __launch_bounds__(BX* BY)
     viscosity_kernel(Range r, int pitch, const double* __restrict__ celldx,
                      const double* __restrict__ celldy, const double* __restrict__ density0,
                      const double* __restrict__ pressure, double* __restrict__ viscosity,
                      const double* __restrict__ xvel0, const double* __restrict__ yvel0) {
-  CLV_THREAD_JK(r);
-  if (!active) return;
-  const size_t c = idx2(pitch, j, k);
-  const double u00 = xvel0[c], u10 = xvel0[c + 1], u01 = xvel0[c + pitch], u11 = xvel0[c + pitch + 1];
-  const double v00 = yvel0[c], v10 = yvel0[c + 1], v01 = yvel0[c + pitch], v11 = yvel0[c + pitch + 1];
-  const double dx = celldx[j + 1], dy = celldy[k + 1];
-  const double ugrad = (u10 + u11) - (u00 + u01);
-  const double vgrad = (v01 + v11) - (v00 + v10);
-  const double div = dx * ugrad + dy * vgrad;
-  const double strain2 = ddiv(0.5 * (u01 + u11 - u00 - u10), dy) + ddiv(0.5 * (v10 + v11 - v00 - v01), dx);
-  double pgradx = ddiv(pressure[c + 1] - pressure[c - 1], dx + celldx[j + 2]);
-  double pgrady = ddiv(pressure[c + pitch] - pressure[c - pitch], dy + celldy[k + 2]);
-  const double pgradx2 = pgradx * pgradx, pgrady2 = pgrady * pgrady;
-  const double limiter =
-      ddiv(ddiv(0.5 * ugrad, dx) * pgradx2 + ddiv(0.5 * vgrad, dy) * pgrady2 + strain2 * pgradx * pgrady,
-           dmax(pgradx2 + pgrady2, 1.0e-16));
-  double q = 0.0;
-  if (!(limiter > 0.0 || div >= 0.0)) {
-    const double ax = dmax(1.0e-16, fabs(pgradx)), ay = dmax(1.0e-16, fabs(pgrady));
-    pgradx = (pgradx < 0.0) ? -ax : ax;
-    pgrady = (pgrady < 0.0) ? -ay : ay;
-    const double pgrad = sqrt(pgradx * pgradx + pgrady * pgrady);
-    const double xgrad = fabs(dx * pgrad / pgradx);
-    const double ygrad = fabs(dy * pgrad / pgrady);
-    const double grad = dmin(xgrad, ygrad);
-    const double grad2 = grad * grad;
-    q = 2.0 * density0[c] * grad2 * limiter * limiter;
+  ViscIn I[NR];
+  CLV_ROWS_BEGIN(r, NR)  // phase 1: every load of every row, back to back
+    const size_t c = idx2(pitch, j, k);
+    ViscIn& in = I[rr_];
+    in.u00 = xvel0[c]; in.u10 = xvel0[c + 1]; in.u01 = xvel0[c + pitch]; in.u11 = xvel0[c + pitch + 1];
+    in.v00 = yvel0[c]; in.v10 = yvel0[c + 1]; in.v01 = yvel0[c + pitch]; in.v11 = yvel0[c + pitch + 1];
+    in.dx = celldx[j + 1]; in.dy = celldy[k + 1]; in.dx1 = celldx[j + 2]; in.dy1 = celldy[k + 2];
+    in.pl = pressure[c - 1]; in.pr = pressure[c + 1]; in.pb = pressure[c - pitch]; in.pt = pressure[c + pitch];
+    in.rho = density0[c];
+    (void)active;
+  CLV_ROWS_END
+  double q[NR];
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < NR; ++i) q[i] = viscosity_cell<false>(I[i], bad);
+  if (bad) {
+#pragma unroll
+    for (int i = 0; i < NR; ++i) q[i] = viscosity_cell<true>(I[i], bad);
   }
-  viscosity[c] = q;
+  {
+    CLV_ROWS_BEGIN(r, NR)
+      if (active) viscosity[idx2(pitch, j, k)] = q[rr_];
+    CLV_ROWS_END
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -153,6 +244,32 @@ __device__ __forceinline__ void block_reduce_publish(double (&v)[N], double* __r
 struct DtParams {
   double g_small, g_big, dtc_safe, dtu_safe, dtv_safe, dtdiv_safe;
 };
+struct DtIn {
+  double dsx, dsy, vol, ssp, visc, rho, u00, u10, u01, u11, v00, v10, v01, v11, xa0, xa1, ya0, ya1;
+};
+// calc_dt_kernel_c.c:99-133, one cell.  The sqrt and the four divisions are independent chains.
+template <bool SAFE>
+__device__ __forceinline__ double calc_dt_cell(const DtIn& I, const DtParams& P, bool& bad) {
+  typedef Math<SAFE> M;
+  double cc = I.ssp * I.ssp;
+  cc = cc + M::div(2.0 * I.visc, I.rho, bad);
+  cc = dmax(M::sqrt(cc, bad), P.g_small);
+  const double dtct = M::div(P.dtc_safe * dmin(I.dsx, I.dsy), cc, bad);
+  double div = 0.0;
+  double dv1 = (I.u00 + I.u01) * I.xa0;
+  double dv2 = (I.u10 + I.u11) * I.xa1;
+  div = div + dv2 - dv1;
+  const double dtut = M::div(P.dtu_safe * 2.0 * I.vol, dmax(fabs(dv1), dmax(fabs(dv2), P.g_small * I.vol)), bad);
+  dv1 = (I.v00 + I.v10) * I.ya0;
+  dv2 = (I.v01 + I.v11) * I.ya1;
+  div = div + dv2 - dv1;
+  const double dtvt = M::div(P.dtv_safe * 2.0 * I.vol, dmax(fabs(dv1), dmax(fabs(dv2), P.g_small * I.vol)), bad);
+  div = M::div(div, 2.0 * I.vol, bad);
+  // the divergence limit applies to compressing cells only: generic operator in that minority branch
+  const double dtdivt = (div < -P.g_small) ? P.dtdiv_safe * (-1.0 / div) : P.g_big;
+  return dmin(dtct, dmin(dtut, dmin(dtvt, dtdivt)));
+}
+template <int NR>
 __global__ void __launch_bounds__(BX* BY)
     calc_dt_kernel(Range r, int pitch, DtParams P, const double* __restrict__ xarea,
                    const double* __restrict__ yarea, const double* __restrict__ celldx,
@@ -161,42 +278,34 @@ __global__ void __launch_bounds__(BX* BY)
                    const double* __restrict__ soundspeed, const double* __restrict__ xvel0,
                    const double* __restrict__ yvel0, double* __restrict__ partials,
                    unsigned int* ticket, double* __restrict__ out) {
-  CLV_THREAD_JK(r);
   double m[1] = {P.g_big};
-  if (active) {
+  CLV_PTILES_BEGIN(r, NR)
     const size_t c = idx2(pitch, j, k);
+    // all loads first (one batch in flight), then the arithmetic
     const double dsx = celldx[j + 1], dsy = celldy[k + 1];
-    const double vol = volume[c];
-    double cc = soundspeed[c] * soundspeed[c];
-    cc = cc + ddiv(2.0 * viscosity[c], density0[c]);
-    cc = dmax(sqrt(cc), P.g_small);
-    const double dtct = P.dtc_safe * dmin(dsx, dsy) / cc;
-    double div = 0.0;
-    double dv1 = (xvel0[c] + xvel0[c + pitch]) * xarea[c];
-    double dv2 = (xvel0[c + 1] + xvel0[c + pitch + 1]) * xarea[c + 1];
-    div = div + dv2 - dv1;
-    const double dtut = P.dtu_safe * 2.0 * vol / dmax(fabs(dv1), dmax(fabs(dv2), P.g_small * vol));
-    dv1 = (yvel0[c] + yvel0[c + 1]) * yarea[c];
-    dv2 = (yvel0[c + pitch] + yvel0[c + pitch + 1]) * yarea[c + pitch];
-    div = div + dv2 - dv1;
-    const double dtvt = P.dtv_safe * 2.0 * vol / dmax(fabs(dv1), dmax(fabs(dv2), P.g_small * vol));
-    div = ddiv(div, 2.0 * vol);
-    const double dtdivt = (div < -P.g_small) ? P.dtdiv_safe * (-1.0 / div) : P.g_big;
-    m[0] = dmin(dtct, dmin(dtut, dmin(dtvt, dtdivt)));
-  }
+    const double vol = volume[c], ssp = soundspeed[c], visc = viscosity[c], rho = density0[c];
+    const double u00 = xvel0[c], u10 = xvel0[c + 1], u01 = xvel0[c + pitch], u11 = xvel0[c + pitch + 1];
+    const double v00 = yvel0[c], v10 = yvel0[c + 1], v01 = yvel0[c + pitch], v11 = yvel0[c + pitch + 1];
+    const double xa0 = xarea[c], xa1 = xarea[c + 1], ya0 = yarea[c], ya1 = yarea[c + pitch];
+    DtIn in{dsx, dsy, vol, ssp, visc, rho, u00, u10, u01, u11, v00, v10, v01, v11, xa0, xa1, ya0, ya1};
+    bool bad = false;
+    double cell_dt = calc_dt_cell<false>(in, P, bad);
+    if (bad) cell_dt = calc_dt_cell<true>(in, P, bad);
+    if (active && cell_dt < m[0]) m[0] = cell_dt;
+  CLV_PTILES_END
   block_reduce_publish<1, true>(m, partials, ticket, out, P.g_big);
 }
 
 // field_summary_kernel_c.c:66-89.  6 passes read = 48 B/cell.
+template <int NR>
 __global__ void __launch_bounds__(BX* BY)
     field_summary_kernel(Range r, int pitch, const double* __restrict__ volume,
                          const double* __restrict__ density0, const double* __restrict__ energy0,
                          const double* __restrict__ pressure, const double* __restrict__ xvel0,
                          const double* __restrict__ yvel0, double* __restrict__ partials,
                          unsigned int* ticket, double* __restrict__ out) {
-  CLV_THREAD_JK(r);
   double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // vol, mass, ie, ke, press
-  if (active) {
+  CLV_PTILES_BEGIN(r, NR)
     const size_t c = idx2(pitch, j, k);
     double vsqrd = 0.0;
     vsqrd = vsqrd + 0.25 * (xvel0[c] * xvel0[c] + yvel0[c] * yvel0[c]);
@@ -205,18 +314,20 @@ __global__ void __launch_bounds__(BX* BY)
     vsqrd = vsqrd + 0.25 * (xvel0[c + pitch + 1] * xvel0[c + pitch + 1] + yvel0[c + pitch + 1] * yvel0[c + pitch + 1]);
     const double cell_vol = volume[c];
     const double cell_mass = cell_vol * density0[c];
-    s[0] = cell_vol;
-    s[1] = cell_mass;
-    s[2] = cell_mass * energy0[c];
-    s[3] = cell_mass * 0.5 * vsqrd;
-    s[4] = cell_vol * pressure[c];
-  }
+    if (active) {
+      s[0] += cell_vol;
+      s[1] += cell_mass;
+      s[2] += cell_mass * energy0[c];
+      s[3] += cell_mass * 0.5 * vsqrd;
+      s[4] += cell_vol * pressure[c];
+    }
+  CLV_PTILES_END
   block_reduce_publish<5, false>(s, partials, ticket, out, 0.0);
 }
 
 // ------------------------------------------------------------------------------------------------
 // PdV_kernel_c.c:63-113 (predictor) / :115-167 (corrector).  11 / 13 passes.
-template <bool PREDICT>
+template <bool PREDICT, int NR>
 __global__ void __launch_bounds__(BX* BY)
     pdv_kernel(Range r, int pitch, double dt, const double* __restrict__ xarea,
                const double* __restrict__ yarea, const double* __restrict__ volume,
@@ -225,63 +336,74 @@ __global__ void __launch_bounds__(BX* BY)
                const double* __restrict__ pressure, const double* __restrict__ viscosity,
                const double* __restrict__ xvel0, const double* __restrict__ xvel1,
                const double* __restrict__ yvel0, const double* __restrict__ yvel1) {
-  CLV_THREAD_JK(r);
-  if (!active) return;
-  const size_t c = idx2(pitch, j, k);
-  const double x00 = xvel0[c], x10 = xvel0[c + 1], x01 = xvel0[c + pitch], x11 = xvel0[c + pitch + 1];
-  const double y00 = yvel0[c], y10 = yvel0[c + 1], y01 = yvel0[c + pitch], y11 = yvel0[c + pitch + 1];
-  double left, right, bottom, top;
-  if (PREDICT) {
-    left = xarea[c] * (x00 + x01 + x00 + x01) * 0.25 * dt * 0.5;
-    right = xarea[c + 1] * (x10 + x11 + x10 + x11) * 0.25 * dt * 0.5;
-    bottom = yarea[c] * (y00 + y10 + y00 + y10) * 0.25 * dt * 0.5;
-    top = yarea[c + pitch] * (y01 + y11 + y01 + y11) * 0.25 * dt * 0.5;
-  } else {
-    const double a00 = xvel1[c], a10 = xvel1[c + 1], a01 = xvel1[c + pitch], a11 = xvel1[c + pitch + 1];
-    const double b00 = yvel1[c], b10 = yvel1[c + 1], b01 = yvel1[c + pitch], b11 = yvel1[c + pitch + 1];
-    left = xarea[c] * (x00 + x01 + a00 + a01) * 0.25 * dt;
-    right = xarea[c + 1] * (x10 + x11 + a10 + a11) * 0.25 * dt;
-    bottom = yarea[c] * (y00 + y10 + b00 + b10) * 0.25 * dt;
-    top = yarea[c + pitch] * (y01 + y11 + b01 + b11) * 0.25 * dt;
-  }
-  const double total = right - left + top - bottom;
-  const double vol = volume[c];
-  const double vc = vol / (vol + total);
-  const double recip = 1.0 / vol;
-  const double rho0 = density0[c];
-  const double de = (pressure[c] / rho0 + ddiv(viscosity[c], rho0)) * total * recip;
-  energy1[c] = energy0[c] - de;
-  density1[c] = rho0 * vc;
+  CLV_ROWS_BEGIN(r, NR)
+    const size_t c = idx2(pitch, j, k);
+    const double x00 = xvel0[c], x10 = xvel0[c + 1], x01 = xvel0[c + pitch], x11 = xvel0[c + pitch + 1];
+    const double y00 = yvel0[c], y10 = yvel0[c + 1], y01 = yvel0[c + pitch], y11 = yvel0[c + pitch + 1];
+    const double vol = volume[c], rho0 = density0[c], pres = pressure[c], visc = viscosity[c], en0 = energy0[c];
+    double left, right, bottom, top;
+    if (PREDICT) {
+      left = xarea[c] * (x00 + x01 + x00 + x01) * 0.25 * dt * 0.5;
+      right = xarea[c + 1] * (x10 + x11 + x10 + x11) * 0.25 * dt * 0.5;
+      bottom = yarea[c] * (y00 + y10 + y00 + y10) * 0.25 * dt * 0.5;
+      top = yarea[c + pitch] * (y01 + y11 + y01 + y11) * 0.25 * dt * 0.5;
+    } else {
+      const double a00 = xvel1[c], a10 = xvel1[c + 1], a01 = xvel1[c + pitch], a11 = xvel1[c + pitch + 1];
+      const double b00 = yvel1[c], b10 = yvel1[c + 1], b01 = yvel1[c + pitch], b11 = yvel1[c + pitch + 1];
+      left = xarea[c] * (x00 + x01 + a00 + a01) * 0.25 * dt;
+      right = xarea[c + 1] * (x10 + x11 + a10 + a11) * 0.25 * dt;
+      bottom = yarea[c] * (y00 + y10 + b00 + b10) * 0.25 * dt;
+      top = yarea[c + pitch] * (y01 + y11 + b01 + b11) * 0.25 * dt;
+    }
+    const double total = right - left + top - bottom;
+    const double vc = vol / (vol + total);
+    const double recip = 1.0 / vol;
+    const double de = (pres / rho0 + ddiv(visc, rho0)) * total * recip;
+    const double e1 = en0 - de;
+    if (active) {
+      energy1[c] = e1;
+      density1[c] = rho0 * vc;
+    }
+  CLV_ROWS_END
 }
 
 // revert_kernel_c.c:46-62 (2 copies) and reset_field_kernel_c.c:46-76 (4 copies)
+template <int NR>
 __global__ void __launch_bounds__(BX* BY)
     copy2_kernel(Range r, int pitch, const double* __restrict__ a_src, double* __restrict__ a_dst,
                  const double* __restrict__ b_src, double* __restrict__ b_dst) {
-  CLV_THREAD_JK(r);
-  if (!active) return;
-  const size_t c = idx2(pitch, j, k);
-  a_dst[c] = a_src[c];
-  b_dst[c] = b_src[c];
+  CLV_ROWS_BEGIN(r, NR)
+    const size_t c = idx2(pitch, j, k);
+    const double a = a_src[c], b = b_src[c];
+    if (active) {
+      a_dst[c] = a;
+      b_dst[c] = b;
+    }
+  CLV_ROWS_END
 }
+template <int NR>
 __global__ void __launch_bounds__(BX* BY)
     reset_field_kernel(Range r, int pitch, int nx, int ny, double* __restrict__ density0,
                        const double* __restrict__ density1, double* __restrict__ energy0,
                        const double* __restrict__ energy1, double* __restrict__ xvel0,
                        const double* __restrict__ xvel1, double* __restrict__ yvel0,
                        const double* __restrict__ yvel1) {
-  CLV_THREAD_JK(r);
-  if (!active) return;
-  const size_t c = idx2(pitch, j, k);
-  if (j <= nx && k <= ny) {
-    density0[c] = density1[c];
-    energy0[c] = energy1[c];
-  }
-  xvel0[c] = xvel1[c];
-  yvel0[c] = yvel1[c];
+  CLV_ROWS_BEGIN(r, NR)
+    const size_t c = idx2(pitch, j, k);
+    const double d = density1[c], e = energy1[c], u = xvel1[c], v = yvel1[c];
+    if (active) {
+      if (j <= nx && k <= ny) {
+        density0[c] = d;
+        energy0[c] = e;
+      }
+      xvel0[c] = u;
+      yvel0[c] = v;
+    }
+  CLV_ROWS_END
 }
 
 // accelerate_kernel_c.c:56-95.  10 passes = 80 B/cell.
+template <int NR>
 __global__ void __launch_bounds__(BX* BY)
     accelerate_kernel(Range r, int pitch, double dt, const double* __restrict__ xarea,
                       const double* __restrict__ yarea, const double* __restrict__ volume,
@@ -289,39 +411,47 @@ __global__ void __launch_bounds__(BX* BY)
                       const double* __restrict__ viscosity, const double* __restrict__ xvel0,
                       const double* __restrict__ yvel0, double* __restrict__ xvel1,
                       double* __restrict__ yvel1) {
-  CLV_THREAD_JK(r);
-  if (!active) return;
-  const size_t c11 = idx2(pitch, j, k), c01 = c11 - 1, c10 = c11 - pitch, c00 = c10 - 1;
-  const double nodal_mass = (density0[c00] * volume[c00] + density0[c10] * volume[c10] +
-                             density0[c11] * volume[c11] + density0[c01] * volume[c01]) * 0.25;
-  const double s = 0.5 * dt / nodal_mass;
-  const double xa1 = xarea[c11], xa0 = xarea[c10];
-  const double ya1 = yarea[c11], ya0 = yarea[c01];
-  const double p11 = pressure[c11], p01 = pressure[c01], p10 = pressure[c10], p00 = pressure[c00];
-  const double q11 = viscosity[c11], q01 = viscosity[c01], q10 = viscosity[c10], q00 = viscosity[c00];
-  double xv = xvel0[c11] - s * (xa1 * (p11 - p01) + xa0 * (p10 - p00));
-  double yv = yvel0[c11] - s * (ya1 * (p11 - p10) + ya0 * (p01 - p00));
-  xv = xv - s * (xa1 * (q11 - q01) + xa0 * (q10 - q00));
-  yv = yv - s * (ya1 * (q11 - q10) + ya0 * (q01 - q00));
-  xvel1[c11] = xv;
-  yvel1[c11] = yv;
+  CLV_ROWS_BEGIN(r, NR)
+    const size_t c11 = idx2(pitch, j, k), c01 = c11 - 1, c10 = c11 - pitch, c00 = c10 - 1;
+    // all loads first (one batch in flight), then the arithmetic
+    const double d00 = density0[c00], d10 = density0[c10], d11 = density0[c11], d01 = density0[c01];
+    const double w00 = volume[c00], w10 = volume[c10], w11 = volume[c11], w01 = volume[c01];
+    const double xa1 = xarea[c11], xa0 = xarea[c10];
+    const double ya1 = yarea[c11], ya0 = yarea[c01];
+    const double p11 = pressure[c11], p01 = pressure[c01], p10 = pressure[c10], p00 = pressure[c00];
+    const double q11 = viscosity[c11], q01 = viscosity[c01], q10 = viscosity[c10], q00 = viscosity[c00];
+    const double xv0 = xvel0[c11], yv0 = yvel0[c11];
+    const double nodal_mass = (d00 * w00 + d10 * w10 + d11 * w11 + d01 * w01) * 0.25;
+    const double s = 0.5 * dt / nodal_mass;
+    double xv = xv0 - s * (xa1 * (p11 - p01) + xa0 * (p10 - p00));
+    double yv = yv0 - s * (ya1 * (p11 - p10) + ya0 * (p01 - p00));
+    xv = xv - s * (xa1 * (q11 - q01) + xa0 * (q10 - q00));
+    yv = yv - s * (ya1 * (q11 - q10) + ya0 * (q01 - q00));
+    if (active) {
+      xvel1[c11] = xv;
+      yvel1[c11] = yv;
+    }
+  CLV_ROWS_END
 }
 
 // flux_calc_kernel_c.c:49-73.  8 passes = 64 B/cell.
+template <int NR>
 __global__ void __launch_bounds__(BX* BY)
     flux_calc_kernel(Range r, int pitch, int nx, int ny, double dt, const double* __restrict__ xarea,
                      const double* __restrict__ yarea, const double* __restrict__ xvel0,
                      const double* __restrict__ yvel0, const double* __restrict__ xvel1,
                      const double* __restrict__ yvel1, double* __restrict__ vol_flux_x,
                      double* __restrict__ vol_flux_y) {
-  CLV_THREAD_JK(r);
-  if (!active) return;
-  const size_t c = idx2(pitch, j, k);
-  const double x0 = xvel0[c], x1 = xvel1[c], y0 = yvel0[c], y1 = yvel1[c];
-  if (k <= ny)
-    vol_flux_x[c] = 0.25 * dt * xarea[c] * (x0 + xvel0[c + pitch] + x1 + xvel1[c + pitch]);
-  if (j <= nx)
-    vol_flux_y[c] = 0.25 * dt * yarea[c] * (y0 + yvel0[c + 1] + y1 + yvel1[c + 1]);
+  CLV_ROWS_BEGIN(r, NR)
+    const size_t c = idx2(pitch, j, k);
+    const double x0 = xvel0[c], x1 = xvel1[c], y0 = yvel0[c], y1 = yvel1[c];
+    const double fx = 0.25 * dt * xarea[c] * (x0 + xvel0[c + pitch] + x1 + xvel1[c + pitch]);
+    const double fy = 0.25 * dt * yarea[c] * (y0 + yvel0[c + 1] + y1 + yvel1[c + 1]);
+    if (active) {
+      if (k <= ny) vol_flux_x[c] = fx;
+      if (j <= nx) vol_flux_y[c] = fy;
+    }
+  CLV_ROWS_END
 }
 
 }  // namespace clv
@@ -340,7 +470,7 @@ void ideal_gas_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* den
   const Range r = make_range(1, g.nx, 1, g.ny);
   {
     LaunchScope ls("ideal_gas");
-    ideal_gas_kernel<<<grid_for(r), dim3(BX, BY), 0, stream()>>>(r, g.pitch, d, e, p, ss);
+    ideal_gas_kernel<NR_IDEAL><<<grid_for(r, NR_IDEAL), dim3(BX, BY), 0, stream()>>>(r, g.pitch, d, e, p, ss);
   }
   finish();
 }
@@ -359,7 +489,8 @@ void viscosity_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* cel
   const Range r = make_range(1, g.nx, 1, g.ny);
   {
     LaunchScope ls("viscosity");
-    viscosity_kernel<<<grid_for(r), dim3(BX, BY), 0, stream()>>>(r, g.pitch, cdx, cdy, d0, p, q, xv, yv);
+    viscosity_kernel<NR_VISC><<<grid_for(r, NR_VISC), dim3(BX, BY), 0, stream()>>>(r, g.pitch, cdx, cdy, d0, p, q,
+                                                                                 xv, yv);
   }
   finish();
 }
@@ -385,14 +516,14 @@ void calc_dt_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* g_sma
   const double* xv = dev(g, xvel0, VERTEX, IN);
   const double* yv = dev(g, yvel0, VERTEX, IN);
   const Range r = make_range(1, g.nx, 1, g.ny);
-  const dim3 grid = grid_for(r);
+  const dim3 grid = persistent_grid(r, NR_DT, 6);
   double* part = partials((size_t)grid.x * grid.y);
   DtParams P{*g_small, *g_big, *dtc_safe, *dtu_safe, *dtv_safe, *dtdiv_safe};
   double* out = host_scalars();
   {
     LaunchScope ls("calc_dt");
-    calc_dt_kernel<<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, P, xa, ya, cdx, cdy, vol, d0, q, ss, xv,
-                                                        yv, part, ticket(), out);
+    calc_dt_kernel<NR_DT><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, P, xa, ya, cdx, cdy, vol, d0, q, ss, xv,
+                                                               yv, part, ticket(), out);
   }
   CLV_CUDA(cudaStreamSynchronize(stream()));  // the one unavoidable host-visible result per step
   const double v = out[0];
@@ -426,16 +557,17 @@ void pdv_kernel_c_(int* prdct, int* xmin, int* xmax, int* ymin, int* ymax, doubl
   const double* x0 = dev(g, xvel0, VERTEX, IN);
   const double* y0 = dev(g, yvel0, VERTEX, IN);
   const Range r = make_range(1, g.nx, 1, g.ny);
+  const dim3 grid = grid_for(r, NR_PDV);
   if (predict) {
     LaunchScope ls("pdv_predict");
-    pdv_kernel<true><<<grid_for(r), dim3(BX, BY), 0, stream()>>>(r, g.pitch, *dt, xa, ya, vol, d0, d1, e0, e1, p,
-                                                                q, x0, x0, y0, y0);
+    pdv_kernel<true, NR_PDV><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, *dt, xa, ya, vol, d0, d1, e0, e1, p, q,
+                                                                  x0, x0, y0, y0);
   } else {
     const double* x1 = dev(g, xvel1, VERTEX, IN);
     const double* y1 = dev(g, yvel1, VERTEX, IN);
     LaunchScope ls("pdv_correct");
-    pdv_kernel<false><<<grid_for(r), dim3(BX, BY), 0, stream()>>>(r, g.pitch, *dt, xa, ya, vol, d0, d1, e0, e1,
-                                                                 p, q, x0, x1, y0, y1);
+    pdv_kernel<false, NR_PDV><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, *dt, xa, ya, vol, d0, d1, e0, e1, p,
+                                                                   q, x0, x1, y0, y1);
   }
   finish();
 }
@@ -450,7 +582,7 @@ void revert_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* densit
   const Range r = make_range(1, g.nx, 1, g.ny);
   {
     LaunchScope ls("revert");
-    copy2_kernel<<<grid_for(r), dim3(BX, BY), 0, stream()>>>(r, g.pitch, d0, d1, e0, e1);
+    copy2_kernel<NR_COPY><<<grid_for(r, NR_COPY), dim3(BX, BY), 0, stream()>>>(r, g.pitch, d0, d1, e0, e1);
   }
   finish();
 }
@@ -470,8 +602,8 @@ void reset_field_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* d
   const Range r = make_range(1, g.nx + 1, 1, g.ny + 1);
   {
     LaunchScope ls("reset_field");
-    reset_field_kernel<<<grid_for(r), dim3(BX, BY), 0, stream()>>>(r, g.pitch, g.nx, g.ny, d0, d1, e0, e1, x0,
-                                                                  x1, y0, y1);
+    reset_field_kernel<NR_RESET><<<grid_for(r, NR_RESET), dim3(BX, BY), 0, stream()>>>(r, g.pitch, g.nx, g.ny, d0, d1,
+                                                                                    e0, e1, x0, x1, y0, y1);
   }
   finish();
 }
@@ -494,8 +626,8 @@ void accelerate_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* dt
   const Range r = make_range(1, g.nx + 1, 1, g.ny + 1);
   {
     LaunchScope ls("accelerate");
-    accelerate_kernel<<<grid_for(r), dim3(BX, BY), 0, stream()>>>(r, g.pitch, *dt, xa, ya, vol, d0, p, q, x0, y0,
-                                                                 x1, y1);
+    accelerate_kernel<NR_ACC><<<grid_for(r, NR_ACC), dim3(BX, BY), 0, stream()>>>(r, g.pitch, *dt, xa, ya, vol, d0, p,
+                                                                                q, x0, y0, x1, y1);
   }
   finish();
 }
@@ -515,8 +647,8 @@ void flux_calc_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* dt,
   const Range r = make_range(1, g.nx + 1, 1, g.ny + 1);
   {
     LaunchScope ls("flux_calc");
-    flux_calc_kernel<<<grid_for(r), dim3(BX, BY), 0, stream()>>>(r, g.pitch, g.nx, g.ny, *dt, xa, ya, x0, y0, x1,
-                                                                y1, fx, fy);
+    flux_calc_kernel<NR_FLUX><<<grid_for(r, NR_FLUX), dim3(BX, BY), 0, stream()>>>(r, g.pitch, g.nx, g.ny, *dt, xa, ya,
+                                                                                 x0, y0, x1, y1, fx, fy);
   }
   finish();
 }
@@ -533,13 +665,13 @@ void field_summary_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double*
   const double* x0 = dev(g, xvel0, VERTEX, IN);
   const double* y0 = dev(g, yvel0, VERTEX, IN);
   const Range r = make_range(1, g.nx, 1, g.ny);
-  const dim3 grid = grid_for(r);
+  const dim3 grid = persistent_grid(r, NR_SUM, 6);
   double* part = partials((size_t)grid.x * grid.y * 5);
   double* out = host_scalars() + 8;
   {
     LaunchScope ls("field_summary");
-    field_summary_kernel<<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, v, d0, e0, p, x0, y0, part,
-                                                              ticket() + 1, out);
+    field_summary_kernel<NR_SUM><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, v, d0, e0, p, x0, y0, part,
+                                                                      ticket() + 1, out);
   }
   CLV_CUDA(cudaStreamSynchronize(stream()));
   *vol = out[0];

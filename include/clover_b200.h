@@ -225,6 +225,12 @@ void clover_b200_profile_reset_(void);
 /* Bytes copied host->device and device->host so far (all modes). */
 void clover_b200_copy_bytes_(long long *h2d, long long *d2h);
 
+/* Self-test of the library's branch-free fp64 div / rcp / sqrt against the compiler's IEEE operators
+ * on *n pseudo-random + adversarial operand pairs: *mismatches must come back 0; *flagged counts
+ * operands the fast sequence hands to the generic path (out of its guarded range). */
+void clover_b200_selftest_math_(long long *n, long long *seed, long long *mismatches, long long *flagged,
+                                long long *checked);
+
 /* Device-side timing for bench.py: record event `slot` (0..7) on the library's stream; elapsed
  * milliseconds between two recorded slots (waits for the later one). */
 void clover_b200_event_record_(int *slot);

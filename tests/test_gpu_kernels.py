@@ -157,3 +157,15 @@ def test_resident_mode_round_trip(b200, oracle_lib):
         b200.clover_b200_download_(ctypes.c_void_p(B[f].ctypes.data))
         assert np.array_equal(A[f], B[f]), f
     b200.clover_b200_invalidate_()
+
+
+def test_fast_math_matches_ieee(b200):
+    """The branch-free div / rcp / sqrt sequences (common.cuh Math<false>) are bit-identical to the
+    compiler's IEEE operators on 3 x 2^28 operands (random over 2^+-600, hydro-like magnitudes,
+    adversarial mantissas, signed zeros); operands outside the guarded range are flagged, not wrong."""
+    n, seed = ctypes.c_longlong(1 << 28), ctypes.c_longlong(20261017)
+    mism, flagged, checked = ctypes.c_longlong(-1), ctypes.c_longlong(-1), ctypes.c_longlong(-1)
+    b200.clover_b200_selftest_math_(ctypes.byref(n), ctypes.byref(seed), ctypes.byref(mism),
+                                    ctypes.byref(flagged), ctypes.byref(checked))
+    assert mism.value == 0, "%d mismatches in %d checked" % (mism.value, checked.value)
+    assert checked.value > 0.9 * 3 * n.value, (checked.value, flagged.value)
