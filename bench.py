@@ -38,7 +38,7 @@ ALG_BYTES_PER_CELL_STEP = 856.0  # 107 fp64 array passes
 KERNEL_PASSES = {
     "ideal_gas": 4, "viscosity": 5, "calc_dt": 8, "pdv_predict": 11, "pdv_correct": 13, "revert": 4,
     "accelerate": 10, "flux_calc": 8, "advec_cell_x": 7.5, "advec_cell_y": 7.5, "advec_mom_x": 4.25,
-    "advec_mom_y": 4.25, "reset_field": 8, "field_summary": 6,
+    "advec_mom_y": 4.25, "advec_mom_x2": 8.5, "advec_mom_y2": 8.5, "reset_field": 8, "field_summary": 6,
 }
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 

@@ -2,8 +2,9 @@
 // Fortran driver (L0/L1 of SURVEY.md), written against the reference's own
 // `*_kernel_c_` C entry points (lowercase + trailing underscore, every argument
 // by reference).  The same driver therefore runs any backend that exports that
-// ABI: the reference's C kernels (oracle/_ref), the plain-C oracle port
-// (oracle/libclover_oracle.so) or the CUDA library (libclover_b200.so).
+// ABI: the CUDA library (libclover_b200.so, the product) or -- in tests and the
+// CPU-baseline leg of bench.py only -- the checkers built under oracle/.  The
+// driver never picks a backend itself: the caller hands it one shared library.
 //
 // No Fortran compiler / MPI exists in this image, so this file stands in for
 // the Fortran driver that "stays" in the north-star design; it contains NO
@@ -200,6 +201,9 @@ struct clover_driver {
   std::vector<SummaryRec> summaries;
   FILE* out = nullptr;
   double wall_hydro = 0;
+  // comm_mode 2: message passing supplied by the host program (MPI in the Fortran original)
+  void (*cb_sendrecv)(int peer, const double* snd, double* rcv, int count) = nullptr;
+  void (*cb_allreduce)(double* values, int n, int op) = nullptr;  // op 0 = min, 1 = sum
 
   void log(const char* fmt, ...) {
     if (!out) return;
@@ -396,7 +400,7 @@ void clover_driver::decompose() {
   for (int cy = 1; cy <= chunk_y; ++cy) {
     for (int cx = 1; cx <= chunk_x; ++cx) {
       int add_x = (cx <= mod_x) ? 1 : 0, add_y = (cy <= mod_y) ? 1 : 0;
-      bool mine = (comm_mode == 0) || (cnk == rank + 1);
+      bool mine = (comm_mode == 0) || (cnk == rank + 1);  // modes 1,2: one chunk per process (rank = chunk-1)
       if (mine) {
         Chunk c;
         c.id = cnk;
@@ -549,6 +553,43 @@ void clover_driver::exchange(const int* fields, int depth) {
     }
     return nullptr;
   };
+  if (comm_mode == 2) {
+    // The reference's own scheme (clover.f90:348-500): pack into HOST buffers with the backend's
+    // pack kernels, exchange them by message passing (callback = MPI_ISEND/IRECV+WAITALL), unpack.
+    Chunk& c = chunks[0];
+    for (int phase = 0; phase < 2; ++phase) {
+      const int fa = phase == 0 ? LEFT : BOTTOM, fb = phase == 0 ? RIGHT : TOP;
+      const int edge = (phase == 0 ? c.y_max : c.x_max) + 5;
+      int nf = 0;
+      for (int f = 0; f < NUM_FIELDS; ++f) nf += (fields[f] == 1);
+      for (int face = fa; face <= fb; ++face) {
+        if (c.neighbours[face] == -1) continue;
+        int off = 0;
+        for (int f = 0; f < NUM_FIELDS; ++f) {
+          if (fields[f] != 1) continue;
+          int ft = field_type[f], o = off;
+          be.packer[face][0](&c.x_min, &c.x_max, &c.y_min, &c.y_max, field_ptr(c, f), c.snd[face], &cd, &vd, &xd,
+                             &yd, &d, &ft, &o);
+          off += depth * edge;
+        }
+      }
+      for (int face = fa; face <= fb; ++face)
+        if (c.neighbours[face] != -1)
+          cb_sendrecv(c.neighbours[face] - 1, c.snd[face], c.rcv[face], nf * depth * edge);
+      for (int face = fa; face <= fb; ++face) {
+        if (c.neighbours[face] == -1) continue;
+        int off = 0;
+        for (int f = 0; f < NUM_FIELDS; ++f) {
+          if (fields[f] != 1) continue;
+          int ft = field_type[f], o = off;
+          be.packer[face][1](&c.x_min, &c.x_max, &c.y_min, &c.y_max, field_ptr(c, f), c.rcv[face], &cd, &vd, &xd,
+                             &yd, &d, &ft, &o);
+          off += depth * edge;
+        }
+      }
+    }
+    return;
+  }
   auto by_id = [&](int id) -> Chunk& {
     for (Chunk& c : chunks)
       if (c.id == id) return c;
@@ -647,6 +688,7 @@ void clover_driver::timestep() {
   }
   dt = std::min(dt, std::min(dtold * deck.dtrise, deck.dtmax));
   if (comm_mode == 1 && nchunks > 1) be.x_min(&dt);  // clover_min, clover.f90:3653
+  if (comm_mode == 2 && nchunks > 1) cb_allreduce(&dt, 1, 0);
   static const char* names[5] = {"", "sound", "xvel", "yvel", "div"};
   log(" Step %7d time %11.7f control %11s timestep  %9.2E%8d,%8d x %9.2E y %9.2E\n", step, time,
       names[(dt_control >= 1 && dt_control <= 4) ? dt_control : 0], dt, jdt, kdt, x_pos, y_pos);
@@ -747,6 +789,7 @@ void clover_driver::field_summary() {
     int n = 5;
     be.x_sum(t, &n);
   }
+  if (comm_mode == 2 && nchunks > 1) cb_allreduce(t, 5, 1);
   SummaryRec r{step, time, t[0], t[1], t[1] / t[0], t[4] / t[0], t[2], t[3], t[2] + t[3]};
   summaries.push_back(r);
   log("\n Time %.16g\n%13s%16s%16s%16s%16s%16s%16s%16s\n", time, "", "Volume", "Mass", "Density",
@@ -805,12 +848,23 @@ clover_driver* clover_driver_create(const char* deck_text, const char* backend_s
 
 const char* clover_driver_error(clover_driver* d) { return d->error.c_str(); }
 
+// comm_mode 2 only: the two message-passing primitives the reference takes from MPI.
+void clover_driver_set_comm_callbacks(clover_driver* d, void (*sendrecv)(int, const double*, double*, int),
+                                      void (*allreduce)(double*, int, int)) {
+  d->cb_sendrecv = sendrecv;
+  d->cb_allreduce = allreduce;
+}
+
 void clover_driver_set_end_step(clover_driver* d, int end_step) { d->deck.end_step = end_step; }
 void clover_driver_set_end_time(clover_driver* d, double end_time) { d->deck.end_time = end_time; }
 void clover_driver_set_summary_frequency(clover_driver* d, int f) { d->deck.summary_frequency = f; }
 
 int clover_driver_start(clover_driver* d) {
   if (!d->error.empty()) return -1;
+  if (d->comm_mode == 2 && d->nchunks > 1 && !(d->cb_sendrecv && d->cb_allreduce)) {
+    d->error = "comm_mode=2 needs clover_driver_set_comm_callbacks";
+    return -1;
+  }
   d->start();
   return d->error.empty() ? 0 : -1;
 }

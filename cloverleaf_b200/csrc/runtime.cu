@@ -140,7 +140,14 @@ void ensure_init() {
 
 cudaStream_t stream() { return R.stream; }
 
+bool is_resident() { return R.resident; }
+
 Grid grid_of(const int* xmin, const int* xmax, const int* ymin, const int* ymax) {
+  flush_deferred();
+  return grid_of_noflush(xmin, xmax, ymin, ymax);
+}
+
+Grid grid_of_noflush(const int* xmin, const int* xmax, const int* ymin, const int* ymax) {
   ensure_init();
   if (*xmin != 1 || *ymin != 1)
     fatal("x_min/y_min must be 1 (start.f90:77-80 always passes 1), got %d/%d", *xmin, *ymin);
@@ -307,6 +314,7 @@ void clover_b200_comm_finalize_internal();
 
 void clover_b200_finalize_(void) {
   if (!R.ready) return;
+  flush_deferred();
   CLV_CUDA(cudaStreamSynchronize(R.stream));
   clover_b200_comm_finalize_internal();
   clover_b200_invalidate_();
@@ -324,12 +332,14 @@ void clover_b200_finalize_(void) {
 
 void clover_b200_set_resident_(int* on) {
   ensure_init();
+  flush_deferred();
   CLV_CUDA(cudaStreamSynchronize(R.stream));
   R.resident = (*on != 0);
 }
 
 void clover_b200_invalidate_(void) {
   if (!R.ready) return;
+  flush_deferred();
   CLV_CUDA(cudaStreamSynchronize(R.stream));
   for (auto& kv : R.arrays) {
     CLV_CUDA(cudaFree(kv.second.d));
@@ -343,6 +353,7 @@ void clover_b200_invalidate_(void) {
 
 void clover_b200_forget_(double* host) {
   if (!R.ready) return;
+  flush_deferred();
   auto it = R.arrays.find(host);
   if (it != R.arrays.end()) {
     CLV_CUDA(cudaStreamSynchronize(R.stream));
@@ -360,6 +371,7 @@ void clover_b200_forget_(double* host) {
 
 void clover_b200_upload_(double* host) {
   ensure_init();
+  flush_deferred();
   auto it = R.arrays.find(host);
   if (it == R.arrays.end()) return;  // never seen: the first use uploads it anyway
   upload(it->second, host);
@@ -367,6 +379,7 @@ void clover_b200_upload_(double* host) {
 
 void clover_b200_download_(double* host) {
   ensure_init();
+  flush_deferred();
   auto it = R.arrays.find(host);
   if (it == R.arrays.end()) fatal("download of an array the library has never seen");
   download(it->second, host);
@@ -375,6 +388,7 @@ void clover_b200_download_(double* host) {
 
 void clover_b200_sync_to_host_(int* fields) {
   ensure_init();
+  flush_deferred();
   if (!C.set) fatal("sync_to_host before register_chunk");
   for (int f = 0; f < 15; ++f) {
     if (fields && fields[f] != 1) continue;
@@ -386,6 +400,7 @@ void clover_b200_sync_to_host_(int* fields) {
 
 void clover_b200_device_synchronize_(void) {
   ensure_init();
+  flush_deferred();
   CLV_CUDA(cudaStreamSynchronize(R.stream));
 }
 

@@ -50,6 +50,7 @@ def _driver_lib():
             ("clover_driver_field", vp, [vp, ci, cs]),
             ("clover_driver_sync_to_host", None, [vp]),
             ("clover_driver_destroy", None, [vp]),
+            ("clover_driver_set_comm_callbacks", None, [vp, vp, vp]),
         ]:
             f = getattr(L, name)
             f.restype = res
@@ -95,6 +96,17 @@ class Driver:
         if summary_frequency is not None:
             L.clover_driver_set_summary_frequency(self._h, int(summary_frequency))
         self.started = False
+
+    SENDRECV = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                                ctypes.POINTER(ctypes.c_double), ctypes.c_int)
+    ALLREDUCE = ctypes.CFUNCTYPE(None, ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int)
+
+    def set_comm_callbacks(self, sendrecv, allreduce):
+        """comm_mode=2: sendrecv(peer, snd, rcv, count) and allreduce(values, n, op[0 min,1 sum]) are
+        Python callables working on ctypes double pointers (what MPI is to the Fortran driver)."""
+        self._cb = (self.SENDRECV(sendrecv), self.ALLREDUCE(allreduce))  # keep alive
+        self._L.clover_driver_set_comm_callbacks(self._h, ctypes.cast(self._cb[0], ctypes.c_void_p),
+                                                 ctypes.cast(self._cb[1], ctypes.c_void_p))
 
     def _check(self):
         err = self._L.clover_driver_error(self._h).decode()
