@@ -31,6 +31,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = os.environ.get("CLV_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
 
 ALG_BYTES_PER_CELL_STEP = 856.0  # 107 fp64 array passes
 # algorithmic array passes per launch (SURVEY.md section 8a "alg" column; advec_mom: half of the fused
