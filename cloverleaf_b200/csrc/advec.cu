@@ -108,6 +108,11 @@ __global__ void __launch_bounds__(32 * ACX_ROWS)
   }
   // stage 1: pre-sweep volume of my cell (valid cells -1..nx+2), and of my left neighbour
   const int jc = clampi(j, -1, nx + 2);
+  if (k + PF_ROWS <= ny) {
+    const size_t pf = idx2(pitch, jc, k + PF_ROWS);
+    prefetch_l2(volume + pf); prefetch_l2(vfx + pf); prefetch_l2(vfy + pf); prefetch_l2(d_old + pf);
+    prefetch_l2(e_old + pf);
+  }
   const double pv = cell_pre_vol_x<SWEEP>(pitch, jc, k, volume, vfx, vfy);
   double pv_left = __shfl_up_sync(0xffffffffu, pv, 1);
   if (lane == 0) pv_left = cell_pre_vol_x<SWEEP>(pitch, clampi(j - 1, -1, nx + 2), k, volume, vfx, vfy);
@@ -214,6 +219,11 @@ __global__ void __launch_bounds__(ACY_THREADS)
     // new row k+2 (clamped at ny+2: MIN(k+1,y_max+2) of :227 for the face k+1)
     const int k2 = (k + 2 < ny + 2) ? k + 2 : ny + 2;
     const size_t c2 = idx2(pitch, j, k2);
+    if (k + PF_MARCH <= ny + 2) {
+      const size_t pf = c + (size_t)PF_MARCH * P;
+      prefetch_l2(d_old + pf); prefetch_l2(e_old + pf); prefetch_l2(vfy + pf); prefetch_l2(volume + pf);
+      if (SWEEP == 1) prefetch_l2(vfx + pf);
+    }
     const double dp2 = d_old[c2], ep2 = e_old[c2];
     const double fy2 = vfy[c + 2 * P];
     const double pv1 = cell_pre_vol_y<SWEEP>(volume[c + P], fy1, fy2, vfx[c + P], vfx[c + P + 1]);
@@ -290,6 +300,12 @@ __global__ void __launch_bounds__(32 * AMX_ROWS)
   const int jn = clampi(j, 0, nx + 2);
   const size_t n = idx2(pitch, jn, k);
   const size_t P = (size_t)pitch;
+  if (k + PF_ROWS <= ny + 1) {
+    const size_t pf = n + (size_t)PF_ROWS * P;
+    prefetch_l2(volume + pf); prefetch_l2(density1 + pf); prefetch_l2(mfx + pf); prefetch_l2(v0_old + pf);
+    if (MOMSWEEP == 1) prefetch_l2(vfy + pf);
+    if (NVEL == 2) prefetch_l2(v1_old + pf);
+  }
   // node_flux (:124-134) and its left neighbour
   const size_t nfi = idx2(pitch, clampi(j, -1, nx + 2), k);
   const double nf = 0.25 * (mfx[nfi - P] + mfx[nfi] + mfx[nfi - P + 1] + mfx[nfi + 1]);
@@ -395,6 +411,12 @@ __global__ void __launch_bounds__(AMY_THREADS)
   }
   // ---- march: k = ks-1 is the priming iteration (computes mom_flux(ks-1), stores nothing) --------
   for (int k = ks - 1; k <= ke; ++k, c += P) {
+    if (k + PF_MARCH <= ny + 2) {
+      const size_t pf = c + (size_t)PF_MARCH * P;
+      prefetch_l2(mfy + pf); prefetch_l2(density1 + pf); prefetch_l2(volume + pf); prefetch_l2(v0_old + pf);
+      if (MOMSWEEP == 2) prefetch_l2(vfx + pf);
+      if (NVEL == 2) prefetch_l2(v1_old + pf);
+    }
     // node_flux(k+1) from mass_flux_y rows k+1 (held) and k+2 (new)
     const double na = mfy[c + 2 * P - 1], nb = mfy[c + 2 * P];
     const double nf1 = 0.25 * (ma1 + mb1 + na + nb);

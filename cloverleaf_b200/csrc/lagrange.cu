@@ -92,6 +92,10 @@ __global__ void __launch_bounds__(BX* BY)
     const size_t c = idx2(pitch, j, k);
     rho[rr_] = density[c];
     en[rr_] = energy[c];
+    if (k + PF_ROWS <= r.k1) {
+      prefetch_l2(density + c + (size_t)PF_ROWS * pitch);
+      prefetch_l2(energy + c + (size_t)PF_ROWS * pitch);
+    }
     (void)active;
   CLV_ROWS_END
   double p[NR], ss[NR];
@@ -166,6 +170,13 @@ __global__ void __launch_bounds__(BX* BY)
     in.dx = celldx[j + 1]; in.dy = celldy[k + 1]; in.dx1 = celldx[j + 2]; in.dy1 = celldy[k + 2];
     in.pl = pressure[c - 1]; in.pr = pressure[c + 1]; in.pb = pressure[c - pitch]; in.pt = pressure[c + pitch];
     in.rho = density0[c];
+    if (k + PF_ROWS <= r.k1) {
+      const size_t pf = c + (size_t)PF_ROWS * pitch;
+      prefetch_l2(xvel0 + pf);
+      prefetch_l2(yvel0 + pf);
+      prefetch_l2(pressure + pf);
+      prefetch_l2(density0 + pf);
+    }
     (void)active;
   CLV_ROWS_END
   double q[NR];
@@ -287,6 +298,11 @@ __global__ void __launch_bounds__(BX* BY)
     const double u00 = xvel0[c], u10 = xvel0[c + 1], u01 = xvel0[c + pitch], u11 = xvel0[c + pitch + 1];
     const double v00 = yvel0[c], v10 = yvel0[c + 1], v01 = yvel0[c + pitch], v11 = yvel0[c + pitch + 1];
     const double xa0 = xarea[c], xa1 = xarea[c + 1], ya0 = yarea[c], ya1 = yarea[c + pitch];
+    if (k + PF_ROWS <= r.k1) {
+      const size_t pf = c + (size_t)PF_ROWS * pitch;
+      prefetch_l2(volume + pf); prefetch_l2(soundspeed + pf); prefetch_l2(viscosity + pf); prefetch_l2(density0 + pf);
+      prefetch_l2(xvel0 + pf); prefetch_l2(yvel0 + pf); prefetch_l2(xarea + pf); prefetch_l2(yarea + pf);
+    }
     DtIn in{dsx, dsy, vol, ssp, visc, rho, u00, u10, u01, u11, v00, v10, v01, v11, xa0, xa1, ya0, ya1};
     bool bad = false;
     double cell_dt = calc_dt_cell<false>(in, P, bad);
@@ -341,6 +357,13 @@ __global__ void __launch_bounds__(BX* BY)
     const double x00 = xvel0[c], x10 = xvel0[c + 1], x01 = xvel0[c + pitch], x11 = xvel0[c + pitch + 1];
     const double y00 = yvel0[c], y10 = yvel0[c + 1], y01 = yvel0[c + pitch], y11 = yvel0[c + pitch + 1];
     const double vol = volume[c], rho0 = density0[c], pres = pressure[c], visc = viscosity[c], en0 = energy0[c];
+    if (k + PF_ROWS <= r.k1) {
+      const size_t pf = c + (size_t)PF_ROWS * pitch;
+      prefetch_l2(xvel0 + pf); prefetch_l2(yvel0 + pf); prefetch_l2(volume + pf); prefetch_l2(density0 + pf);
+      prefetch_l2(pressure + pf); prefetch_l2(viscosity + pf); prefetch_l2(energy0 + pf); prefetch_l2(xarea + pf);
+      prefetch_l2(yarea + pf);
+      if (!PREDICT) { prefetch_l2(xvel1 + pf); prefetch_l2(yvel1 + pf); }
+    }
     double left, right, bottom, top;
     if (PREDICT) {
       left = xarea[c] * (x00 + x01 + x00 + x01) * 0.25 * dt * 0.5;
@@ -375,6 +398,10 @@ __global__ void __launch_bounds__(BX* BY)
   CLV_ROWS_BEGIN(r, NR)
     const size_t c = idx2(pitch, j, k);
     const double a = a_src[c], b = b_src[c];
+    if (k + PF_ROWS <= r.k1) {
+      prefetch_l2(a_src + c + (size_t)PF_ROWS * pitch);
+      prefetch_l2(b_src + c + (size_t)PF_ROWS * pitch);
+    }
     if (active) {
       a_dst[c] = a;
       b_dst[c] = b;
@@ -391,6 +418,10 @@ __global__ void __launch_bounds__(BX* BY)
   CLV_ROWS_BEGIN(r, NR)
     const size_t c = idx2(pitch, j, k);
     const double d = density1[c], e = energy1[c], u = xvel1[c], v = yvel1[c];
+    if (k + PF_ROWS <= r.k1) {
+      const size_t pf = c + (size_t)PF_ROWS * pitch;
+      prefetch_l2(density1 + pf); prefetch_l2(energy1 + pf); prefetch_l2(xvel1 + pf); prefetch_l2(yvel1 + pf);
+    }
     if (active) {
       if (j <= nx && k <= ny) {
         density0[c] = d;
@@ -421,6 +452,11 @@ __global__ void __launch_bounds__(BX* BY)
     const double p11 = pressure[c11], p01 = pressure[c01], p10 = pressure[c10], p00 = pressure[c00];
     const double q11 = viscosity[c11], q01 = viscosity[c01], q10 = viscosity[c10], q00 = viscosity[c00];
     const double xv0 = xvel0[c11], yv0 = yvel0[c11];
+    if (k + PF_ROWS <= r.k1) {
+      const size_t pf = c11 + (size_t)PF_ROWS * pitch;
+      prefetch_l2(density0 + pf); prefetch_l2(volume + pf); prefetch_l2(xarea + pf); prefetch_l2(yarea + pf);
+      prefetch_l2(pressure + pf); prefetch_l2(viscosity + pf); prefetch_l2(xvel0 + pf); prefetch_l2(yvel0 + pf);
+    }
     const double nodal_mass = (d00 * w00 + d10 * w10 + d11 * w11 + d01 * w01) * 0.25;
     const double s = 0.5 * dt / nodal_mass;
     double xv = xv0 - s * (xa1 * (p11 - p01) + xa0 * (p10 - p00));
@@ -445,6 +481,11 @@ __global__ void __launch_bounds__(BX* BY)
   CLV_ROWS_BEGIN(r, NR)
     const size_t c = idx2(pitch, j, k);
     const double x0 = xvel0[c], x1 = xvel1[c], y0 = yvel0[c], y1 = yvel1[c];
+    if (k + PF_ROWS <= r.k1) {
+      const size_t pf = c + (size_t)PF_ROWS * pitch;
+      prefetch_l2(xvel0 + pf); prefetch_l2(xvel1 + pf); prefetch_l2(yvel0 + pf); prefetch_l2(yvel1 + pf);
+      prefetch_l2(xarea + pf); prefetch_l2(yarea + pf);
+    }
     const double fx = 0.25 * dt * xarea[c] * (x0 + xvel0[c + pitch] + x1 + xvel1[c + pitch]);
     const double fy = 0.25 * dt * yarea[c] * (y0 + yvel0[c + 1] + y1 + yvel1[c + 1]);
     if (active) {
