@@ -449,20 +449,11 @@ __global__ void __launch_bounds__(AMY_THREADS)
 
 }  // namespace clv
 
-using namespace clv;
+namespace clv {
 
-extern "C" {
-
-void advec_cell_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, int* dir, int* sweep_number,
-                          double* vertexdx, double* vertexdy, double* volume, double* density1,
-                          double* energy1, double* mass_flux_x, double* vol_flux_x,
-                          double* mass_flux_y, double* vol_flux_y, double* pre_vol, double* post_vol,
-                          double* pre_mass, double* post_mass, double* advec_vol, double* post_ener,
-                          double* ener_flux) {
-  (void)pre_vol; (void)post_vol; (void)pre_mass; (void)post_mass; (void)advec_vol; (void)post_ener; (void)ener_flux;
-  const Grid g = grid_of(xmin, xmax, ymin, ymax);
-  const int sweep = *sweep_number;
-  if ((*dir != 1 && *dir != 2) || (sweep != 1 && sweep != 2)) fatal("advec_cell: dir=%d sweep=%d", *dir, sweep);
+void run_advec_cell(const Grid& g, int dir, int sweep, double* vertexdx, double* vertexdy, double* volume,
+                    double* density1, double* energy1, double* mass_flux_x, double* vol_flux_x,
+                    double* mass_flux_y, double* vol_flux_y) {
   const double* vol = dev(g, volume, CELL, IN);
   const double* fx = dev(g, vol_flux_x, XFACE, IN);
   const double* fy = dev(g, vol_flux_y, YFACE, IN);
@@ -470,7 +461,7 @@ void advec_cell_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, int* dir, 
   const double* e_old = dev(g, energy1, CELL, INOUT);
   double* d_new = dev_alt(g, density1, CELL);
   double* e_new = dev_alt(g, energy1, CELL);
-  if (*dir == 1) {
+  if (dir == 1) {
     const double* vdx = dev(g, vertexdx, X1D_VERT, IN);
     double* mf = dev(g, mass_flux_x, XFACE, OUT);
     const dim3 grid((unsigned)((g.nx + 4 + 30) / 31), (unsigned)((g.ny + 4 + ACX_ROWS - 1) / ACX_ROWS));
@@ -496,38 +487,26 @@ void advec_cell_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, int* dir, 
   }
   swap_alt(density1);
   swap_alt(energy1);
-  finish();
 }
 
-// advec_mom is called twice per sweep with identical arguments except the velocity component
-// (advec_mom_driver.f90:85,108: xvel1 then yvel1).  Node fluxes, node masses and the upwind choice are
-// the same for both, so in resident mode the which_vel==1 call is only RECORDED and the which_vel==2
-// call launches one kernel that advects both components (9 instead of 14 array passes, one set of
-// node-mass arithmetic).  Anything else that touches the library first (any other entry point, a
-// download, a mode switch) flushes the recorded call through flush_deferred().
-struct PendingMom {
-  bool active = false;
-  Grid g{};
-  int dirn = 0, sweep = 0;
-  double *vel1 = nullptr, *mfx = nullptr, *vfx = nullptr, *mfy = nullptr, *vfy = nullptr, *vol = nullptr,
-         *d1 = nullptr, *cdx = nullptr, *cdy = nullptr;
-};
-static PendingMom g_pend;
-
-static void launch_advec_mom(const PendingMom& a, double* vel_a, double* vel_b) {
-  const Grid& g = a.g;
-  const int mom_sweep = a.dirn + 2 * (a.sweep - 1);
-  const double* vol = dev(g, a.vol, CELL, IN);
-  const double* d1 = dev(g, a.d1, CELL, IN);
-  const double* fx = dev(g, a.vfx, XFACE, IN);
-  const double* fy = dev(g, a.vfy, YFACE, IN);
+// One launch advects vel_a and, when vel_b != nullptr, vel_b as well (advec_mom is called twice per sweep with
+// identical arguments except the velocity component, advec_mom_driver.f90:85,108; node fluxes, node masses
+// and the upwind choice are the same for both).
+void run_advec_mom(const Grid& g, int dirn, int sweep, double* vel_a, double* vel_b, double* mass_flux_x,
+                   double* vol_flux_x, double* mass_flux_y, double* vol_flux_y, double* volume, double* density1,
+                   double* celldx, double* celldy) {
+  const int mom_sweep = dirn + 2 * (sweep - 1);
+  const double* vol = dev(g, volume, CELL, IN);
+  const double* d1 = dev(g, density1, CELL, IN);
+  const double* fx = dev(g, vol_flux_x, XFACE, IN);
+  const double* fy = dev(g, vol_flux_y, YFACE, IN);
   const double* va_old = dev(g, vel_a, VERTEX, INOUT);
   double* va_new = dev_alt(g, vel_a, VERTEX);
   const double* vb_old = vel_b ? dev(g, vel_b, VERTEX, INOUT) : nullptr;
   double* vb_new = vel_b ? dev_alt(g, vel_b, VERTEX) : nullptr;
-  if (a.dirn == 1) {
-    const double* cdx = dev(g, a.cdx, X1D_CELL, IN);
-    const double* mf = dev(g, a.mfx, XFACE, IN);
+  if (dirn == 1) {
+    const double* cdx = dev(g, celldx, X1D_CELL, IN);
+    const double* mf = dev(g, mass_flux_x, XFACE, IN);
     const dim3 grid((unsigned)((g.nx + 5 + 29) / 30), (unsigned)((g.ny + 5 + AMX_ROWS - 1) / AMX_ROWS));
     const dim3 block(32, AMX_ROWS);
     LaunchScope ls(vel_b ? "advec_mom_x2" : "advec_mom_x");
@@ -538,8 +517,8 @@ static void launch_advec_mom(const PendingMom& a, double* vel_a, double* vel_b) 
     else                { if (vel_b) CLV_MOMX(3, 2); else CLV_MOMX(3, 1); }
 #undef CLV_MOMX
   } else {
-    const double* cdy = dev(g, a.cdy, Y1D_CELL, IN);
-    const double* mf = dev(g, a.mfy, YFACE, IN);
+    const double* cdy = dev(g, celldy, Y1D_CELL, IN);
+    const double* mf = dev(g, mass_flux_y, YFACE, IN);
     const dim3 grid((unsigned)((g.nx + 4 + XOFF + AMY_THREADS) / AMY_THREADS),
                     (unsigned)((g.ny + 1 + AMY_SEG - 1) / AMY_SEG));
     LaunchScope ls(vel_b ? "advec_mom_y2" : "advec_mom_y");
@@ -554,6 +533,39 @@ static void launch_advec_mom(const PendingMom& a, double* vel_a, double* vel_b) 
   if (vel_b) swap_alt(vel_b);
 }
 
+}  // namespace clv
+
+using namespace clv;
+
+extern "C" {
+
+// Op::a = {vertexdx, vertexdy, volume, density1, energy1, mass_flux_x, vol_flux_x, mass_flux_y, vol_flux_y};
+// iv = {dir, sweep}
+void advec_cell_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, int* dir, int* sweep_number,
+                          double* vertexdx, double* vertexdy, double* volume, double* density1,
+                          double* energy1, double* mass_flux_x, double* vol_flux_x,
+                          double* mass_flux_y, double* vol_flux_y, double* pre_vol, double* post_vol,
+                          double* pre_mass, double* post_mass, double* advec_vol, double* post_ener,
+                          double* ener_flux) {
+  (void)pre_vol; (void)post_vol; (void)pre_mass; (void)post_mass; (void)advec_vol; (void)post_ener; (void)ener_flux;
+  Op op;
+  op.kind = OP_ADVEC_CELL;
+  const Grid g = op.g = grid_of_noflush(xmin, xmax, ymin, ymax);
+  const int d = op.iv[0] = *dir, sweep = op.iv[1] = *sweep_number;
+  if ((d != 1 && d != 2) || (sweep != 1 && sweep != 2)) fatal("advec_cell: dir=%d sweep=%d", d, sweep);
+  double* a[] = {vertexdx, vertexdy, volume, density1, energy1, mass_flux_x, vol_flux_x, mass_flux_y, vol_flux_y};
+  for (double* p : a) op.a[op.na++] = p;
+  op.reads({vertexdx, vertexdy, volume, density1, energy1, vol_flux_x, vol_flux_y});
+  op.writes({density1, energy1, d == 1 ? mass_flux_x : mass_flux_y});
+  op.run = [=] {
+    run_advec_cell(g, d, sweep, vertexdx, vertexdy, volume, density1, energy1, mass_flux_x, vol_flux_x, mass_flux_y,
+                   vol_flux_y);
+  };
+  submit(std::move(op));
+}
+
+// Op::a = {vel1, mass_flux_x, vol_flux_x, mass_flux_y, vol_flux_y, volume, density1, celldx, celldy};
+// iv = {which_vel, sweep, direction}
 void advec_mom_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* vel1, double* mass_flux_x,
                          double* vol_flux_x, double* mass_flux_y, double* vol_flux_y, double* volume,
                          double* density1, double* node_flux, double* node_mass_post,
@@ -561,49 +573,22 @@ void advec_mom_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* vel
                          double* celldx, double* celldy, int* which_vel, int* sweep_number,
                          int* direction) {
   (void)node_flux; (void)node_mass_post; (void)node_mass_pre; (void)mom_flux; (void)pre_vol; (void)post_vol;
-  PendingMom now;
-  now.g = grid_of_noflush(xmin, xmax, ymin, ymax);
-  now.dirn = *direction;
-  now.sweep = *sweep_number;
-  now.vel1 = vel1; now.mfx = mass_flux_x; now.vfx = vol_flux_x; now.mfy = mass_flux_y; now.vfy = vol_flux_y;
-  now.vol = volume; now.d1 = density1; now.cdx = celldx; now.cdy = celldy;
-  const int mom_sweep = now.dirn + 2 * (now.sweep - 1);
-  if ((now.dirn != 1 && now.dirn != 2) || mom_sweep < 1 || mom_sweep > 4)
-    fatal("advec_mom: direction=%d sweep=%d", now.dirn, now.sweep);
-  if (g_pend.active) {
-    const PendingMom& p = g_pend;
-    const bool pair = (*which_vel == 2) && p.g.nx == now.g.nx && p.g.ny == now.g.ny && p.dirn == now.dirn &&
-                      p.sweep == now.sweep && p.mfx == now.mfx && p.vfx == now.vfx && p.mfy == now.mfy &&
-                      p.vfy == now.vfy && p.vol == now.vol && p.d1 == now.d1 && p.cdx == now.cdx &&
-                      p.cdy == now.cdy && p.vel1 != now.vel1;
-    if (pair) {
-      g_pend.active = false;
-      launch_advec_mom(now, p.vel1, now.vel1);
-      finish();
-      return;
-    }
-    flush_deferred();
-  }
-  // measured on B200 (profiles/): the fused x kernel beats two single-component launches (0.40 vs
-  // 0.48 ms at 3840^2); the fused y march does not yet (0.42 vs 0.32 ms, register pressure), so only x
-  // sweeps are deferred for now.
-  if (*which_vel == 1 && is_resident() && now.dirn == 1) {
-    g_pend = now;
-    g_pend.active = true;
-    return;
-  }
-  launch_advec_mom(now, vel1, nullptr);
-  finish();
+  Op op;
+  op.kind = OP_ADVEC_MOM;
+  const Grid g = op.g = grid_of_noflush(xmin, xmax, ymin, ymax);
+  const int dirn = *direction, sweep = *sweep_number;
+  op.iv[0] = *which_vel; op.iv[1] = sweep; op.iv[2] = dirn;
+  const int mom_sweep = dirn + 2 * (sweep - 1);
+  if ((dirn != 1 && dirn != 2) || mom_sweep < 1 || mom_sweep > 4) fatal("advec_mom: direction=%d sweep=%d", dirn, sweep);
+  double* a[] = {vel1, mass_flux_x, vol_flux_x, mass_flux_y, vol_flux_y, volume, density1, celldx, celldy};
+  for (double* p : a) op.a[op.na++] = p;
+  op.reads({vel1, mass_flux_x, vol_flux_x, mass_flux_y, vol_flux_y, volume, density1, celldx, celldy});
+  op.writes({vel1});
+  op.run = [=] {
+    run_advec_mom(g, dirn, sweep, vel1, nullptr, mass_flux_x, vol_flux_x, mass_flux_y, vol_flux_y, volume, density1,
+                  celldx, celldy);
+  };
+  submit(std::move(op));
 }
 
 }  // extern "C"
-
-namespace clv {
-// Launch a recorded single-component advec_mom call (see PendingMom above).
-void flush_deferred() {
-  if (!g_pend.active) return;
-  const PendingMom p = g_pend;
-  g_pend.active = false;
-  launch_advec_mom(p, p.vel1, nullptr);
-}
-}  // namespace clv

@@ -1,0 +1,503 @@
+// fuse.cu -- several reference calls in ONE kernel (resident mode, see "deferred execution" in common.cuh).
+//
+// runtime.cu hands fuse_at() the recorded calls of one stretch of the hydro step.  The patterns below are the
+// runs of calls that the reference driver always makes back to back (hydro.f90:52-64, timestep.f90:56-117,
+// PdV.f90:46-138, advection.f90:43-110) and whose intermediates no other call reads:
+//
+//   T  ideal_gas(d0,e0) -> [exchange][update_halo]{d0,e0,p,u0,v0; depth 1} -> viscosity
+//        -> [exchange][update_halo]{q; depth 1} -> calc_dt
+//      one kernel: pressure of the four neighbours is recomputed from their density/energy (2 multiplies,
+//      bit-identical to the exchanged/reflected halo pressure because p is a pointwise function and the
+//      reflection of cell data is a plain copy), soundspeed and viscosity go straight into the dt minimum.
+//      17 algorithmic passes -> 10 (reads d0,e0,u0,v0,volume,xarea,yarea; writes p,q,soundspeed).
+//   P  PdV predictor -> ideal_gas(d1,e1) -> [exchange][update_halo]{p} -> revert
+//      one kernel: the predicted density/energy live in registers only (revert would overwrite them);
+//      19 passes -> 10 or 11 (soundspeed is stored only if something reads it before it is next overwritten).
+//   C  accelerate -> PdV corrector -> flux_calc
+//      one kernel: a CTA computes the new velocities of its vertex tile (+1 row, +1 column) into shared
+//      memory, then the cells and faces of the tile take them from there; 31 passes -> 15.
+//   M  advec_mom(xvel1) -> advec_mom(yvel1), same sweep: one launch for both components.
+//
+// Every fused kernel executes the same per-cell arithmetic, in the same order, as the single-call kernels
+// (lagrange.cuh), so every array the host can observe afterwards is bit-identical (tests/test_gpu_run.py,
+// tests/test_gpu_fusion.py run both ways and compare all 15 fields including halos).
+#include "clover_b200.h"
+#include "common.cuh"
+#include "lagrange.cuh"
+
+namespace clv {
+
+// from runtime.cu
+bool chunk_registered();
+const int* chunk_neighbours();
+
+// ================================================================================================
+// T: ideal_gas + viscosity + calc_dt.  Persistent CTAs over 32x8 tiles (as calc_dt), one cell per thread.
+// The thread of cell (j,k) evaluates the equation of state for its own cell (pressure, soundspeed) and the
+// pressures of its four face neighbours; threads on the rim of the chunk also store the neighbour's
+// pressure into the depth-1 halo ring (what the halo update of `pressure` would have put there).
+template <bool SAFE>
+__device__ __forceinline__ double timestep_cell(double rho, double en, ViscIn& V, DtIn& D, const DtParams& P,
+                                                double& p, double& ss, double& q, bool& bad) {
+  ideal_gas_cell<SAFE>(rho, en, p, ss, bad);
+  q = viscosity_cell<SAFE>(V, bad);
+  D.ssp = ss;
+  D.visc = q;
+  return calc_dt_cell<SAFE>(D, P, bad);
+}
+
+template <bool WRITE_SS>
+__global__ void __launch_bounds__(BX* BY)
+    timestep_kernel(Range r, int pitch, DtParams P, const double* __restrict__ xarea,
+                    const double* __restrict__ yarea, const double* __restrict__ celldx,
+                    const double* __restrict__ celldy, const double* __restrict__ volume,
+                    const double* __restrict__ density0, const double* __restrict__ energy0,
+                    double* __restrict__ pressure, double* __restrict__ viscosity,
+                    double* __restrict__ soundspeed, const double* __restrict__ xvel0,
+                    const double* __restrict__ yvel0, double* __restrict__ partials, unsigned int* ticket,
+                    double* __restrict__ out) {
+  double m[1] = {P.g_big};
+  CLV_PTILES_BEGIN(r, 1)
+    const size_t c = idx2(pitch, j, k);
+    // all loads first (one batch in flight), then the arithmetic
+    const double rho = density0[c], en = energy0[c];
+    const double rl = density0[c - 1], rr = density0[c + 1], rb = density0[c - pitch], rt = density0[c + pitch];
+    const double el = energy0[c - 1], er = energy0[c + 1], eb = energy0[c - pitch], et = energy0[c + pitch];
+    const double u00 = xvel0[c], u10 = xvel0[c + 1], u01 = xvel0[c + pitch], u11 = xvel0[c + pitch + 1];
+    const double v00 = yvel0[c], v10 = yvel0[c + 1], v01 = yvel0[c + pitch], v11 = yvel0[c + pitch + 1];
+    const double dsx = celldx[j + 1], dsy = celldy[k + 1], dsx1 = celldx[j + 2], dsy1 = celldy[k + 2];
+    const double vol = volume[c];
+    const double xa0 = xarea[c], xa1 = xarea[c + 1], ya0 = yarea[c], ya1 = yarea[c + pitch];
+    if (k + PF_ROWS <= r.k1) {
+      const size_t pf = c + (size_t)PF_ROWS * pitch;
+      prefetch_l2(density0 + pf); prefetch_l2(energy0 + pf); prefetch_l2(xvel0 + pf); prefetch_l2(yvel0 + pf);
+      prefetch_l2(volume + pf); prefetch_l2(xarea + pf); prefetch_l2(yarea + pf);
+    }
+    // ideal_gas_kernel_c.c:52 for the four neighbours
+    const double pl = (1.4 - 1.0) * rl * el, pr = (1.4 - 1.0) * rr * er;
+    const double pb = (1.4 - 1.0) * rb * eb, pt = (1.4 - 1.0) * rt * et;
+    ViscIn V{u00, u10, u01, u11, v00, v10, v01, v11, dsx, dsy, dsx1, dsy1, pl, pr, pb, pt, rho};
+    DtIn D{dsx, dsy, vol, 0.0, 0.0, rho, u00, u10, u01, u11, v00, v10, v01, v11, xa0, xa1, ya0, ya1};
+    bool bad = false;
+    double p, ss, q;
+    double cell_dt = timestep_cell<false>(rho, en, V, D, P, p, ss, q, bad);
+    if (bad) cell_dt = timestep_cell<true>(rho, en, V, D, P, p, ss, q, bad);
+    if (active) {
+      pressure[c] = p;
+      viscosity[c] = q;
+      if (WRITE_SS) soundspeed[c] = ss;
+      if (cell_dt < m[0]) m[0] = cell_dt;
+      // depth-1 halo ring of pressure (corners by the corner cells)
+      const bool L = (j == r.j0), R_ = (j == r.j1), B = (k == r.k0), T = (k == r.k1);
+      if (L) pressure[c - 1] = pl;
+      if (R_) pressure[c + 1] = pr;
+      if (B) pressure[c - pitch] = pb;
+      if (T) pressure[c + pitch] = pt;
+      if ((L || R_) && (B || T)) {
+        const size_t cc = c + (L ? -1 : 1) + (B ? -(ptrdiff_t)pitch : (ptrdiff_t)pitch);
+        pressure[cc] = (1.4 - 1.0) * density0[cc] * energy0[cc];
+        // a one-cell-wide or one-cell-high chunk: the same cell is on both rims
+        if (L && R_) { const size_t c2 = c + 1 + (B ? -(ptrdiff_t)pitch : (ptrdiff_t)pitch); pressure[c2] = (1.4 - 1.0) * density0[c2] * energy0[c2]; }
+        if (B && T) { const size_t c2 = c + (L ? -1 : 1) + (ptrdiff_t)pitch; pressure[c2] = (1.4 - 1.0) * density0[c2] * energy0[c2]; }
+        if (L && R_ && B && T) { const size_t c2 = c + 1 + (ptrdiff_t)pitch; pressure[c2] = (1.4 - 1.0) * density0[c2] * energy0[c2]; }
+      }
+    }
+  CLV_PTILES_END
+  block_reduce_publish<1, true>(m, partials, ticket, out, P.g_big);
+}
+
+// ================================================================================================
+// P: PdV predictor (PdV_kernel_c.c:63-113) + ideal_gas on the predicted state (ideal_gas_kernel_c.c:48-59).
+// The predicted density1/energy1 are not stored: revert (revert_kernel_c.c:46-62) replaces them right after.
+constexpr int NR_PRED = 2;
+template <bool WRITE_SS>
+__global__ void __launch_bounds__(BX* BY)
+    pdv_predict_eos_kernel(Range r, int pitch, double dt, const double* __restrict__ xarea,
+                           const double* __restrict__ yarea, const double* __restrict__ volume,
+                           const double* __restrict__ density0, const double* __restrict__ energy0,
+                           double* __restrict__ pressure, const double* __restrict__ viscosity,
+                           double* __restrict__ soundspeed, const double* __restrict__ xvel0,
+                           const double* __restrict__ yvel0) {
+  CLV_ROWS_BEGIN(r, NR_PRED)
+    const size_t c = idx2(pitch, j, k);
+    const double x00 = xvel0[c], x10 = xvel0[c + 1], x01 = xvel0[c + pitch], x11 = xvel0[c + pitch + 1];
+    const double y00 = yvel0[c], y10 = yvel0[c + 1], y01 = yvel0[c + pitch], y11 = yvel0[c + pitch + 1];
+    const double vol = volume[c], rho0 = density0[c], pres = pressure[c], visc = viscosity[c], en0 = energy0[c];
+    const double xa0 = xarea[c], xa1 = xarea[c + 1], ya0 = yarea[c], ya1 = yarea[c + pitch];
+    if (k + PF_ROWS <= r.k1) {
+      const size_t pf = c + (size_t)PF_ROWS * pitch;
+      prefetch_l2(xvel0 + pf); prefetch_l2(yvel0 + pf); prefetch_l2(volume + pf); prefetch_l2(density0 + pf);
+      prefetch_l2(pressure + pf); prefetch_l2(viscosity + pf); prefetch_l2(energy0 + pf); prefetch_l2(xarea + pf);
+      prefetch_l2(yarea + pf);
+    }
+    const double left = xa0 * (x00 + x01 + x00 + x01) * 0.25 * dt * 0.5;
+    const double right = xa1 * (x10 + x11 + x10 + x11) * 0.25 * dt * 0.5;
+    const double bottom = ya0 * (y00 + y10 + y00 + y10) * 0.25 * dt * 0.5;
+    const double top = ya1 * (y01 + y11 + y01 + y11) * 0.25 * dt * 0.5;
+    const double total = right - left + top - bottom;
+    const double vc = vol / (vol + total);
+    const double recip = 1.0 / vol;
+    const double de = (pres / rho0 + ddiv(visc, rho0)) * total * recip;
+    const double e1 = en0 - de;
+    const double d1 = rho0 * vc;
+    bool bad = false;
+    double p, ss;
+    ideal_gas_cell<false>(d1, e1, p, ss, bad);
+    if (bad) ideal_gas_cell<true>(d1, e1, p, ss, bad);
+    if (active) {
+      pressure[c] = p;
+      if (WRITE_SS) soundspeed[c] = ss;
+    }
+  CLV_ROWS_END
+}
+
+// ================================================================================================
+// C: accelerate (accelerate_kernel_c.c:56-95) + PdV corrector (PdV_kernel_c.c:115-167) + flux_calc
+// (flux_calc_kernel_c.c:49-73).  A CTA owns the slots (j,k) of a CT_W x CT_H tile of 1..nx+1 x 1..ny+1;
+// slot (j,k) = vertex (j,k), x-face (j,k), y-face (j,k) and cell (j,k).  Phase 1: new velocities of the
+// tile's vertices plus one extra row and column (the upper/right vertices of the last cells) go to shared
+// memory together with the old ones; phase 2: faces and cells read their two / four vertices from there.
+constexpr int CT_W = 64, CT_H = 16, CT_BY = 4, CT_NR = CT_H / CT_BY;
+struct CorrectArgs {
+  const double *xarea, *yarea, *volume, *density0, *energy0, *pressure, *viscosity, *xvel0, *yvel0;
+  double *xvel1, *yvel1, *density1, *energy1, *vol_flux_x, *vol_flux_y;
+};
+__device__ __forceinline__ void accel_vertex(const CorrectArgs& A, size_t c11, int pitch, double dt, double& xv0,
+                                             double& yv0, double& xv, double& yv) {
+  const size_t c01 = c11 - 1, c10 = c11 - pitch, c00 = c10 - 1;
+  const double d00 = A.density0[c00], d10 = A.density0[c10], d11 = A.density0[c11], d01 = A.density0[c01];
+  const double w00 = A.volume[c00], w10 = A.volume[c10], w11 = A.volume[c11], w01 = A.volume[c01];
+  const double xa1 = A.xarea[c11], xa0 = A.xarea[c10];
+  const double ya1 = A.yarea[c11], ya0 = A.yarea[c01];
+  const double p11 = A.pressure[c11], p01 = A.pressure[c01], p10 = A.pressure[c10], p00 = A.pressure[c00];
+  const double q11 = A.viscosity[c11], q01 = A.viscosity[c01], q10 = A.viscosity[c10], q00 = A.viscosity[c00];
+  xv0 = A.xvel0[c11];
+  yv0 = A.yvel0[c11];
+  const double nodal_mass = (d00 * w00 + d10 * w10 + d11 * w11 + d01 * w01) * 0.25;
+  const double s = 0.5 * dt / nodal_mass;
+  xv = xv0 - s * (xa1 * (p11 - p01) + xa0 * (p10 - p00));
+  yv = yv0 - s * (ya1 * (p11 - p10) + ya0 * (p01 - p00));
+  xv = xv - s * (xa1 * (q11 - q01) + xa0 * (q10 - q00));
+  yv = yv - s * (ya1 * (q11 - q10) + ya0 * (q01 - q00));
+}
+
+__global__ void __launch_bounds__(CT_W* CT_BY)
+    lagrange_correct_kernel(CorrectArgs A, int nx, int ny, int pitch, double dt) {
+  __shared__ double su0[CT_H + 1][CT_W + 1], sv0[CT_H + 1][CT_W + 1], su1[CT_H + 1][CT_W + 1], sv1[CT_H + 1][CT_W + 1];
+  const int lx = threadIdx.x, ty = threadIdx.y;
+  const int j0 = 1 + (int)blockIdx.x * CT_W, k0 = 1 + (int)blockIdx.y * CT_H;
+  const int jmax = nx + 1, kmax = ny + 1;
+  // ---- phase 1: vertices --------------------------------------------------------------------------------
+#pragma unroll
+  for (int i = 0; i < CT_NR; ++i) {
+    const int ly = ty + i * CT_BY;
+    const int jr = j0 + lx, kr = k0 + ly;
+    const int j = jr <= jmax ? jr : jmax, k = kr <= kmax ? kr : kmax;  // clamped: always safe to load
+    const size_t c = idx2(pitch, j, k);
+    if (kr + PF_ROWS <= kmax) {
+      const size_t pf = c + (size_t)PF_ROWS * pitch;
+      prefetch_l2(A.density0 + pf); prefetch_l2(A.volume + pf); prefetch_l2(A.pressure + pf);
+      prefetch_l2(A.viscosity + pf); prefetch_l2(A.xarea + pf); prefetch_l2(A.yarea + pf);
+      prefetch_l2(A.xvel0 + pf); prefetch_l2(A.yvel0 + pf); prefetch_l2(A.energy0 + pf);
+    }
+    double xv0, yv0, xv, yv;
+    accel_vertex(A, c, pitch, dt, xv0, yv0, xv, yv);
+    su0[ly][lx] = xv0; sv0[ly][lx] = yv0; su1[ly][lx] = xv; sv1[ly][lx] = yv;
+    if (jr <= jmax && kr <= kmax) {
+      A.xvel1[c] = xv;
+      A.yvel1[c] = yv;
+    }
+  }
+  {
+    // the extra row (ly = CT_H, lx = 0..CT_W) and column (lx = CT_W, ly = 0..CT_H-1): owned by the neighbour tiles
+    const int t = ty * CT_W + lx;
+    if (t < CT_W + 1 + CT_H) {
+      const int ex = t <= CT_W ? t : CT_W, ey = t <= CT_W ? CT_H : t - (CT_W + 1);
+      const int jr = j0 + ex, kr = k0 + ey;
+      const int j = jr <= jmax ? jr : jmax, k = kr <= kmax ? kr : kmax;
+      double xv0, yv0, xv, yv;
+      accel_vertex(A, idx2(pitch, j, k), pitch, dt, xv0, yv0, xv, yv);
+      su0[ey][ex] = xv0; sv0[ey][ex] = yv0; su1[ey][ex] = xv; sv1[ey][ex] = yv;
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: faces and cells ----------------------------------------------------------------------------
+#pragma unroll
+  for (int i = 0; i < CT_NR; ++i) {
+    const int ly = ty + i * CT_BY;
+    const int j = j0 + lx, k = k0 + ly;
+    if (j > jmax || k > kmax) continue;
+    const size_t c = idx2(pitch, j, k);
+    const double x00 = su0[ly][lx], x10 = su0[ly][lx + 1], x01 = su0[ly + 1][lx], x11 = su0[ly + 1][lx + 1];
+    const double y00 = sv0[ly][lx], y10 = sv0[ly][lx + 1], y01 = sv0[ly + 1][lx], y11 = sv0[ly + 1][lx + 1];
+    const double a00 = su1[ly][lx], a10 = su1[ly][lx + 1], a01 = su1[ly + 1][lx], a11 = su1[ly + 1][lx + 1];
+    const double b00 = sv1[ly][lx], b10 = sv1[ly][lx + 1], b01 = sv1[ly + 1][lx], b11 = sv1[ly + 1][lx + 1];
+    const double xa0 = A.xarea[c], ya0 = A.yarea[c];
+    // flux_calc_kernel_c.c:55-58, :67-70
+    if (k <= ny) A.vol_flux_x[c] = 0.25 * dt * xa0 * (x00 + x01 + a00 + a01);
+    if (j <= nx) A.vol_flux_y[c] = 0.25 * dt * ya0 * (y00 + y10 + b00 + b10);
+    if (j <= nx && k <= ny) {
+      // PdV_kernel_c.c:117-163
+      const double xa1 = A.xarea[c + 1], ya1 = A.yarea[c + pitch];
+      const double vol = A.volume[c], rho0 = A.density0[c], pres = A.pressure[c], visc = A.viscosity[c];
+      const double en0 = A.energy0[c];
+      const double left = xa0 * (x00 + x01 + a00 + a01) * 0.25 * dt;
+      const double right = xa1 * (x10 + x11 + a10 + a11) * 0.25 * dt;
+      const double bottom = ya0 * (y00 + y10 + b00 + b10) * 0.25 * dt;
+      const double top = ya1 * (y01 + y11 + b01 + b11) * 0.25 * dt;
+      const double total = right - left + top - bottom;
+      const double vc = vol / (vol + total);
+      const double recip = 1.0 / vol;
+      const double de = (pres / rho0 + ddiv(visc, rho0)) * total * recip;
+      A.energy1[c] = en0 - de;
+      A.density1[c] = rho0 * vc;
+    }
+  }
+}
+
+// single-call host launchers (lagrange.cu, advec.cu)
+void run_revert(const Grid& g, double* density0, double* density1, double* energy0, double* energy1);
+void run_advec_mom(const Grid& g, int dirn, int sweep, double* vel_a, double* vel_b, double* mass_flux_x,
+                   double* vol_flux_x, double* mass_flux_y, double* vol_flux_y, double* volume, double* density1,
+                   double* celldx, double* celldy);
+
+static bool same_grid(const Op& a, const Op& b) { return a.g.nx == b.g.nx && a.g.ny == b.g.ny; }
+
+// ---- M: advec_mom pair ------------------------------------------------------------------------------------
+static size_t fuse_mom_pair(const Op* q, size_t n, size_t i) {
+  if (i + 1 >= n) return 0;
+  const Op &x = q[i], &y = q[i + 1];
+  if (x.kind != OP_ADVEC_MOM || y.kind != OP_ADVEC_MOM || !same_grid(x, y)) return 0;
+  if (x.iv[0] != 1 || y.iv[0] != 2 || x.iv[1] != y.iv[1] || x.iv[2] != y.iv[2]) return 0;
+  for (int k = 1; k < 9; ++k)
+    if (x.a[k] != y.a[k]) return 0;
+  if (x.a[0] == y.a[0]) return 0;
+  // measured on B200 (profiles/): the two-component x kernel beats two launches (0.31 vs 0.40 ms at 3840^2),
+  // the two-component y march does not (register pressure), so only x sweeps are paired
+  if (x.iv[2] != 1) return 0;
+  run_advec_mom(x.g, x.iv[2], x.iv[1], x.a[0], y.a[0], x.a[1], x.a[2], x.a[3], x.a[4], x.a[5], x.a[6], x.a[7], x.a[8]);
+  return 2;
+}
+
+// ---- helpers for the halo ops inside a pattern ---------------------------------------------------------------
+enum FieldId { F_DENSITY0 = 0, F_DENSITY1, F_ENERGY0, F_ENERGY1, F_PRESSURE, F_VISCOSITY, F_SOUNDSPEED, F_XVEL0,
+               F_XVEL1, F_YVEL0, F_YVEL1 };
+static bool halo_mask_is(const Op& o, std::initializer_list<int> ids, int depth) {
+  if (o.iv[0] != depth) return false;
+  int want[15] = {};
+  for (int f : ids) want[f] = 1;
+  for (int f = 0; f < 15; ++f)
+    if ((o.fields[f] != 0) != (want[f] != 0)) return false;
+  return true;
+}
+static HaloArgs halo_args(const Op& o, int drop_field) {
+  HaloArgs h;
+  for (int f = 0; f < 15; ++f) {
+    h.host[f] = o.a[f];
+    h.fields[f] = (f == drop_field) ? 0 : o.fields[f];
+  }
+  h.depth = o.iv[0];
+  for (int f = 0; f < 4; ++f) h.ext[f] = o.iv[1 + f];
+  return h;
+}
+// Optional [exchange][update_halo] pair with the given field set starting at q[i]; returns how many ops it is.
+// `covered` reports whether all four faces of the chunk get their halo from these ops (neighbour faces from the
+// exchange, external faces from update_halo).
+static size_t match_halo(const Op* q, size_t n, size_t i, const Grid& g, std::initializer_list<int> ids, int depth,
+                         const Op** ex, const Op** uh, bool* covered) {
+  *ex = *uh = nullptr;
+  size_t used = 0;
+  if (i + used < n && q[i + used].kind == OP_EXCHANGE && halo_mask_is(q[i + used], ids, depth) &&
+      q[i + used].g.nx == g.nx && q[i + used].g.ny == g.ny)
+    *ex = &q[i + used++];
+  if (i + used < n && q[i + used].kind == OP_UPDATE_HALO && halo_mask_is(q[i + used], ids, depth) &&
+      q[i + used].g.nx == g.nx && q[i + used].g.ny == g.ny)
+    *uh = &q[i + used++];
+  if (covered) {
+    int nb[4] = {-1, -1, -1, -1};
+    if (chunk_registered())
+      for (int f = 0; f < 4; ++f) nb[f] = chunk_neighbours()[f];
+    bool all = true;
+    for (int f = 0; f < 4; ++f) {
+      const bool by_exchange = (*ex != nullptr) && nb[f] != -1;
+      const bool by_reflect = (*uh != nullptr) && (*uh)->iv[1 + f] != 0;
+      all = all && (by_exchange || by_reflect);
+    }
+    *covered = all;
+  }
+  return used;
+}
+// Is the value stored into `arr` by the op(s) before q[from] dead, i.e. fully overwritten before anything in the
+// rest of the recorded stretch reads it?  (End of the stretch = the host may look = not dead.)
+static bool dead_after(const Op* q, size_t n, size_t from, const double* arr) {
+  for (size_t k = from; k < n; ++k) {
+    if (q[k].does_read(arr)) return false;
+    if (q[k].does_overwrite(arr)) return true;
+    if (q[k].touches(arr)) return false;
+  }
+  return false;
+}
+
+static int g_ctas_per_sm_timestep[2] = {0, 0};
+
+// ---- T: ideal_gas -> halo{d0,e0,p,u0,v0} -> viscosity -> halo{q} -> calc_dt -------------------------------------
+static size_t fuse_timestep(const Op* q, size_t n, size_t i) {
+  const Op& ig = q[i];
+  if (ig.kind != OP_IDEAL_GAS) return 0;
+  const Grid g = ig.g;
+  size_t k = i + 1;
+  const Op *ex1, *uh1, *ex2, *uh2;
+  bool covered = false;
+  k += match_halo(q, n, k, g, {F_DENSITY0, F_ENERGY0, F_PRESSURE, F_XVEL0, F_YVEL0}, 1, &ex1, &uh1, &covered);
+  if (!covered || k >= n || q[k].kind != OP_VISCOSITY || !same_grid(ig, q[k])) return 0;
+  const Op& vi = q[k++];
+  k += match_halo(q, n, k, g, {F_VISCOSITY}, 1, &ex2, &uh2, nullptr);
+  if (k >= n || q[k].kind != OP_CALC_DT || !same_grid(ig, q[k])) return 0;
+  const Op& dt = q[k++];
+  // the same arrays all the way through
+  double *density0 = ig.a[0], *energy0 = ig.a[1], *pressure = ig.a[2], *soundspeed = ig.a[3];
+  double *celldx = vi.a[0], *celldy = vi.a[1], *viscosity = vi.a[4], *xvel0 = vi.a[5], *yvel0 = vi.a[6];
+  if (vi.a[2] != density0 || vi.a[3] != pressure) return 0;
+  if (dt.a[2] != celldx || dt.a[3] != celldy || dt.a[5] != density0 || dt.a[6] != viscosity || dt.a[7] != soundspeed ||
+      dt.a[8] != xvel0 || dt.a[9] != yvel0)
+    return 0;
+  for (const Op* h : {ex1, uh1})
+    if (h && (h->a[F_DENSITY0] != density0 || h->a[F_ENERGY0] != energy0 || h->a[F_PRESSURE] != pressure ||
+              h->a[F_XVEL0] != xvel0 || h->a[F_YVEL0] != yvel0))
+      return 0;
+  for (const Op* h : {ex2, uh2})
+    if (h && h->a[F_VISCOSITY] != viscosity) return 0;
+  double *xarea = dt.a[0], *yarea = dt.a[1], *volume = dt.a[4];
+
+  // halos of density0, energy0, xvel0, yvel0 first (pressure's ring is produced by the kernel itself)
+  if (ex1) run_exchange(g, halo_args(*ex1, F_PRESSURE));
+  if (uh1) run_update_halo(g, halo_args(*uh1, F_PRESSURE));
+  {
+    const double* xa = dev(g, xarea, XFACE, IN);
+    const double* ya = dev(g, yarea, YFACE, IN);
+    const double* cdx = dev(g, celldx, X1D_CELL, IN);
+    const double* cdy = dev(g, celldy, Y1D_CELL, IN);
+    const double* vol = dev(g, volume, CELL, IN);
+    const double* d0 = dev(g, density0, CELL, IN);
+    const double* e0 = dev(g, energy0, CELL, IN);
+    double* p = dev(g, pressure, CELL, OUT);
+    double* qv = dev(g, viscosity, CELL, OUT);
+    double* ss = dev(g, soundspeed, CELL, OUT);
+    const double* xv = dev(g, xvel0, VERTEX, IN);
+    const double* yv = dev(g, yvel0, VERTEX, IN);
+    const DtParams P{dt.sv[0], dt.sv[1], dt.sv[2], dt.sv[3], dt.sv[4], dt.sv[5]};
+    const Range r = make_range(1, g.nx, 1, g.ny);
+    if (!g_ctas_per_sm_timestep[0]) {
+      CLV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_ctas_per_sm_timestep[0], timestep_kernel<true>,
+                                                             BX * BY, 0));
+      if (g_ctas_per_sm_timestep[0] < 1) g_ctas_per_sm_timestep[0] = 1;
+    }
+    const dim3 grid = persistent_grid(r, 1, g_ctas_per_sm_timestep[0]);
+    double* part = partials((size_t)grid.x * grid.y);
+    LaunchScope ls("timestep_fused");
+    timestep_kernel<true><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, P, xa, ya, cdx, cdy, vol, d0, e0, p, qv, ss,
+                                                               xv, yv, part, ticket(), host_scalars());
+  }
+  if (ex2) run_exchange(g, halo_args(*ex2, -1));
+  if (uh2) run_update_halo(g, halo_args(*uh2, -1));
+  return k - i;
+}
+
+// ---- P: PdV predictor -> ideal_gas(d1,e1) -> halo{p} -> revert ---------------------------------------------------
+static size_t fuse_predict(const Op* q, size_t n, size_t i) {
+  const Op& pv = q[i];
+  if (pv.kind != OP_PDV_PREDICT || i + 2 >= n) return 0;
+  const Op& ig = q[i + 1];
+  if (ig.kind != OP_IDEAL_GAS || !same_grid(pv, ig)) return 0;
+  const Grid g = pv.g;
+  double *xarea = pv.a[0], *yarea = pv.a[1], *volume = pv.a[2], *density0 = pv.a[3], *density1 = pv.a[4],
+         *energy0 = pv.a[5], *energy1 = pv.a[6], *pressure = pv.a[7], *viscosity = pv.a[8], *xvel0 = pv.a[9],
+         *yvel0 = pv.a[11];
+  if (ig.a[0] != density1 || ig.a[1] != energy1 || ig.a[2] != pressure) return 0;
+  double* soundspeed = ig.a[3];
+  size_t k = i + 2;
+  const Op *ex, *uh;
+  k += match_halo(q, n, k, g, {F_PRESSURE}, 1, &ex, &uh, nullptr);
+  for (const Op* h : {ex, uh})
+    if (h && h->a[F_PRESSURE] != pressure) return 0;
+  if (k >= n || q[k].kind != OP_REVERT || !same_grid(pv, q[k])) return 0;
+  const Op& rv = q[k++];
+  if (rv.a[0] != density0 || rv.a[1] != density1 || rv.a[2] != energy0 || rv.a[3] != energy1) return 0;
+  const bool write_ss = !dead_after(q, n, i + 2, soundspeed);
+  {
+    const double* xa = dev(g, xarea, XFACE, IN);
+    const double* ya = dev(g, yarea, YFACE, IN);
+    const double* vol = dev(g, volume, CELL, IN);
+    const double* d0 = dev(g, density0, CELL, IN);
+    const double* e0 = dev(g, energy0, CELL, IN);
+    double* p = dev(g, pressure, CELL, INOUT);
+    const double* qv = dev(g, viscosity, CELL, IN);
+    double* ss = dev(g, soundspeed, CELL, OUT);
+    const double* x0 = dev(g, xvel0, VERTEX, IN);
+    const double* y0 = dev(g, yvel0, VERTEX, IN);
+    const Range r = make_range(1, g.nx, 1, g.ny);
+    const dim3 grid = grid_for(r, NR_PRED);
+    LaunchScope ls("pdv_predict_fused");
+    if (write_ss)
+      pdv_predict_eos_kernel<true><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, pv.sv[0], xa, ya, vol, d0, e0, p, qv,
+                                                                        ss, x0, y0);
+    else
+      pdv_predict_eos_kernel<false><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, pv.sv[0], xa, ya, vol, d0, e0, p,
+                                                                         qv, ss, x0, y0);
+  }
+  if (ex) run_exchange(g, halo_args(*ex, -1));
+  if (uh) run_update_halo(g, halo_args(*uh, -1));
+  run_revert(g, density0, density1, energy0, energy1);  // a lazy copy in resident mode
+  return k - i;
+}
+
+// ---- C: accelerate -> PdV corrector -> flux_calc -------------------------------------------------------------------
+static size_t fuse_correct(const Op* q, size_t n, size_t i) {
+  if (i + 2 >= n) return 0;
+  const Op &ac = q[i], &pv = q[i + 1], &fc = q[i + 2];
+  if (ac.kind != OP_ACCELERATE || pv.kind != OP_PDV_CORRECT || fc.kind != OP_FLUX_CALC) return 0;
+  if (!same_grid(ac, pv) || !same_grid(ac, fc) || ac.sv[0] != pv.sv[0] || ac.sv[0] != fc.sv[0]) return 0;
+  const Grid g = ac.g;
+  double *xarea = ac.a[0], *yarea = ac.a[1], *volume = ac.a[2], *density0 = ac.a[3], *pressure = ac.a[4],
+         *viscosity = ac.a[5], *xvel0 = ac.a[6], *yvel0 = ac.a[7], *xvel1 = ac.a[8], *yvel1 = ac.a[9];
+  double *density1 = pv.a[4], *energy0 = pv.a[5], *energy1 = pv.a[6];
+  if (pv.a[0] != xarea || pv.a[1] != yarea || pv.a[2] != volume || pv.a[3] != density0 || pv.a[7] != pressure ||
+      pv.a[8] != viscosity || pv.a[9] != xvel0 || pv.a[10] != xvel1 || pv.a[11] != yvel0 || pv.a[12] != yvel1)
+    return 0;
+  if (fc.a[0] != xarea || fc.a[1] != yarea || fc.a[2] != xvel0 || fc.a[3] != yvel0 || fc.a[4] != xvel1 ||
+      fc.a[5] != yvel1)
+    return 0;
+  double *vol_flux_x = fc.a[6], *vol_flux_y = fc.a[7];
+  CorrectArgs A;
+  A.xarea = dev(g, xarea, XFACE, IN);
+  A.yarea = dev(g, yarea, YFACE, IN);
+  A.volume = dev(g, volume, CELL, IN);
+  A.density0 = dev(g, density0, CELL, IN);
+  A.energy0 = dev(g, energy0, CELL, IN);
+  A.pressure = dev(g, pressure, CELL, IN);
+  A.viscosity = dev(g, viscosity, CELL, IN);
+  A.xvel0 = dev(g, xvel0, VERTEX, IN);
+  A.yvel0 = dev(g, yvel0, VERTEX, IN);
+  A.xvel1 = dev(g, xvel1, VERTEX, OUT_FULL);
+  A.yvel1 = dev(g, yvel1, VERTEX, OUT_FULL);
+  A.density1 = dev(g, density1, CELL, OUT_FULL);
+  A.energy1 = dev(g, energy1, CELL, OUT_FULL);
+  A.vol_flux_x = dev(g, vol_flux_x, XFACE, OUT);
+  A.vol_flux_y = dev(g, vol_flux_y, YFACE, OUT);
+  const dim3 grid((unsigned)((g.nx + 1 + CT_W - 1) / CT_W), (unsigned)((g.ny + 1 + CT_H - 1) / CT_H));
+  LaunchScope ls("lagrange_correct_fused");
+  lagrange_correct_kernel<<<grid, dim3(CT_W, CT_BY), 0, stream()>>>(A, g.nx, g.ny, g.pitch, ac.sv[0]);
+  return 3;
+}
+
+size_t fuse_at(const Op* q, size_t n, size_t i) {
+  switch (q[i].kind) {
+    case OP_ADVEC_MOM: return fuse_mom_pair(q, n, i);
+    case OP_IDEAL_GAS: return fuse_timestep(q, n, i);
+    case OP_PDV_PREDICT: return fuse_predict(q, n, i);
+    case OP_ACCELERATE: return fuse_correct(q, n, i);
+    default: return 0;
+  }
+}
+
+}  // namespace clv

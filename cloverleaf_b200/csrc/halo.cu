@@ -156,7 +156,7 @@ static void abi_message(int face, bool unpack, int* xmin, int* xmax, int* ymin, 
   const size_t lo = (size_t)F.offset;
   const size_t span = (size_t)((face < 2 ? g.ny + F.y_inc : g.nx + F.x_inc) + 2 * depth);
   const size_t hi = lo + span * depth;
-  F.p = dev(g, field, kind, unpack ? INOUT : IN);
+  F.p = dev(g, field, kind, unpack ? INOUT_HALO : IN);
   double* dbuf = dev_buffer(buffer, hi, unpack ? IN : 0, lo, hi);
   launch_message(unpack, T, g, depth, face, dbuf);
   if (!unpack) {
@@ -319,6 +319,64 @@ __global__ void generate_chunk_kernel(States S, int nx, int ny, int pitch, const
   if (set) { xvel0[c] = u; yvel0[c] = v; }
 }
 
+// ---- update_halo and the NCCL exchange on their own (host side) ---------------------------------------
+static FieldTable field_table(const Grid& g, const HaloArgs& h, int depth, int edge) {
+  FieldTable T;
+  T.n = 0;
+  int off = 0;
+  for (int f = 0; f < 15; ++f) {
+    if (!h.fields[f]) continue;
+    FieldDesc& F = T.f[T.n++];
+    F.p = dev(g, h.host[f], kFieldGeom[f].kind, INOUT_HALO);
+    F.x_inc = kFieldGeom[f].x_inc; F.y_inc = kFieldGeom[f].y_inc; F.m = kFieldGeom[f].m;
+    F.sx = kFieldGeom[f].sx; F.sy = kFieldGeom[f].sy;
+    F.offset = off;  // clover.f90:368-375: per-field offsets are running sums of depth*(edge+5)
+    off += depth * edge;
+  }
+  return T;
+}
+
+void run_update_halo(const Grid& g, const HaloArgs& h) {
+  const FieldTable T = field_table(g, h, h.depth, 0);
+  if (T.n > 0 && (h.ext[0] || h.ext[1] || h.ext[2] || h.ext[3])) {
+    const int ring = 2 * h.depth * (g.nx + 1 + 2 * h.depth) + 2 * h.depth * (g.ny + 1);
+    const dim3 grid((unsigned)((ring + 255) / 256), (unsigned)T.n);
+    LaunchScope ls("update_halo");
+    update_halo_kernel<<<grid, 256, 0, stream()>>>(T, g.nx, g.ny, g.pitch, h.depth, h.ext[0], h.ext[1], h.ext[2],
+                                                   h.ext[3]);
+  }
+}
+
+void run_exchange(const Grid& g, const HaloArgs& h) {
+  const int* nb = chunk_neighbours();
+  const int depth = h.depth;
+  for (int phase = 0; phase < 2; ++phase) {
+    const int fa = phase * 2, fb = fa + 1;
+    if (nb[fa] == -1 && nb[fb] == -1) continue;
+    const int edge = (phase == 0 ? g.ny : g.nx) + 5;
+    const FieldTable T = field_table(g, h, depth, edge);
+    if (T.n == 0) return;
+    const size_t total = (size_t)T.n * depth * edge;
+    for (int face = fa; face <= fb; ++face) {
+      if (nb[face] == -1) continue;
+      ensure_msg_buffers(face, (size_t)15 * 2 * edge);
+      launch_message(false, T, g, depth, face, N.snd[face]);
+    }
+    CLV_NCCL(N.GroupStart());
+    for (int face = fa; face <= fb; ++face) {
+      if (nb[face] == -1) continue;
+      const int peer = nb[face] - 1;  // rank = chunk - 1 (clover.f90:892)
+      CLV_NCCL(N.Send(N.snd[face], total, ncclDouble, peer, N.comm, stream()));
+      CLV_NCCL(N.Recv(N.rcv[face], total, ncclDouble, peer, N.comm, stream()));
+    }
+    CLV_NCCL(N.GroupEnd());
+    for (int face = fa; face <= fb; ++face) {
+      if (nb[face] == -1) continue;
+      launch_message(true, T, g, depth, face, N.rcv[face]);
+    }
+  }
+}
+
 }  // namespace clv
 
 using namespace clv;
@@ -331,29 +389,26 @@ void update_halo_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, int* chun
                            double* xvel0, double* yvel0, double* xvel1, double* yvel1, double* vol_flux_x,
                            double* vol_flux_y, double* mass_flux_x, double* mass_flux_y, int* fields,
                            int* depth_p) {
-  const Grid g = grid_of(xmin, xmax, ymin, ymax);
-  const int depth = *depth_p;
+  // Op::a[0..14] = the 15 fields in field-id order (data.f90:51-66); fields = mask; iv = {depth, ext[4]}
+  Op op;
+  op.kind = OP_UPDATE_HALO;
+  const Grid g = op.g = grid_of_noflush(xmin, xmax, ymin, ymax);
+  const int depth = op.iv[0] = *depth_p;
   if (depth < 1 || depth > 2) fatal("update_halo: depth %d", depth);
-  int ext[4];
-  for (int f = 0; f < 4; ++f) ext[f] = (chunk_neighbours[f] == -1 && tile_neighbours[f] == -1);
+  for (int f = 0; f < 4; ++f) op.iv[1 + f] = (chunk_neighbours[f] == -1 && tile_neighbours[f] == -1);
   double* host[15] = {density0, density1, energy0, energy1, pressure, viscosity, soundspeed, xvel0,
                       xvel1, yvel0, yvel1, vol_flux_x, vol_flux_y, mass_flux_x, mass_flux_y};
-  FieldTable T;
-  T.n = 0;
+  HaloArgs h;
   for (int f = 0; f < 15; ++f) {
-    if (fields[f] != 1) continue;
-    FieldDesc& F = T.f[T.n++];
-    F.p = dev(g, host[f], kFieldGeom[f].kind, INOUT);
-    F.x_inc = kFieldGeom[f].x_inc; F.y_inc = kFieldGeom[f].y_inc; F.m = kFieldGeom[f].m;
-    F.sx = kFieldGeom[f].sx; F.sy = kFieldGeom[f].sy; F.offset = 0;
+    op.a[f] = h.host[f] = host[f];
+    op.fields[f] = h.fields[f] = (fields[f] == 1);
+    if (h.fields[f]) { op.reads({host[f]}); op.writes({host[f]}); }
   }
-  if (T.n > 0 && (ext[0] || ext[1] || ext[2] || ext[3])) {
-    const int ring = 2 * depth * (g.nx + 1 + 2 * depth) + 2 * depth * (g.ny + 1);
-    const dim3 grid((unsigned)((ring + 255) / 256), (unsigned)T.n);
-    LaunchScope ls("update_halo");
-    update_halo_kernel<<<grid, 256, 0, stream()>>>(T, g.nx, g.ny, g.pitch, depth, ext[0], ext[1], ext[2], ext[3]);
-  }
-  finish();
+  op.na = 15;
+  h.depth = depth;
+  for (int f = 0; f < 4; ++f) h.ext[f] = op.iv[1 + f];
+  op.run = [=] { run_update_halo(g, h); };
+  submit(std::move(op));
 }
 
 #define CLV_PACK_ENTRY(name, face, unpack)                                                          \
@@ -416,51 +471,27 @@ void clover_b200_exchange_(int* fields, int* depth_p) {
   const int* nb = chunk_neighbours();
   if (nb[0] == -1 && nb[1] == -1 && nb[2] == -1 && nb[3] == -1) return;
   if (!N.comm) fatal("exchange with neighbours but no communicator (call clover_b200_comm_init_)");
-  const int depth = *depth_p;
+  // Op::a[0..14] = the registered chunk's 15 fields; fields = mask; iv[0] = depth
+  Op op;
+  op.kind = OP_EXCHANGE;
   int one = 1, nx = chunk_nx(), ny = chunk_ny();
-  const Grid g = grid_of(&one, &nx, &one, &ny);
-  // clover.f90:368-375: per-field offsets are running sums of depth*(edge+5)
-  for (int phase = 0; phase < 2; ++phase) {
-    const int fa = phase * 2, fb = fa + 1;
-    if (nb[fa] == -1 && nb[fb] == -1) continue;
-    const int edge = (phase == 0 ? g.ny : g.nx) + 5;
-    FieldTable T;
-    T.n = 0;
-    int off = 0;
-    for (int f = 0; f < 15; ++f) {
-      if (fields[f] != 1) continue;
-      FieldDesc& F = T.f[T.n++];
-      F.p = dev(g, chunk_field_host(f), kFieldGeom[f].kind, INOUT);
-      F.x_inc = kFieldGeom[f].x_inc; F.y_inc = kFieldGeom[f].y_inc; F.m = kFieldGeom[f].m;
-      F.sx = kFieldGeom[f].sx; F.sy = kFieldGeom[f].sy;
-      F.offset = off;
-      off += depth * edge;
-    }
-    if (T.n == 0) return;
-    const size_t total = (size_t)off;
-    for (int face = fa; face <= fb; ++face) {
-      if (nb[face] == -1) continue;
-      ensure_msg_buffers(face, (size_t)15 * 2 * edge);
-      launch_message(false, T, g, depth, face, N.snd[face]);
-    }
-    CLV_NCCL(N.GroupStart());
-    for (int face = fa; face <= fb; ++face) {
-      if (nb[face] == -1) continue;
-      const int peer = nb[face] - 1;  // rank = chunk - 1 (clover.f90:892)
-      CLV_NCCL(N.Send(N.snd[face], total, ncclDouble, peer, N.comm, stream()));
-      CLV_NCCL(N.Recv(N.rcv[face], total, ncclDouble, peer, N.comm, stream()));
-    }
-    CLV_NCCL(N.GroupEnd());
-    for (int face = fa; face <= fb; ++face) {
-      if (nb[face] == -1) continue;
-      launch_message(true, T, g, depth, face, N.rcv[face]);
-    }
+  const Grid g = op.g = grid_of_noflush(&one, &nx, &one, &ny);
+  const int depth = op.iv[0] = *depth_p;
+  HaloArgs h;
+  for (int f = 0; f < 15; ++f) {
+    op.a[f] = h.host[f] = chunk_field_host(f);
+    op.fields[f] = h.fields[f] = (fields[f] == 1);
+    if (h.fields[f]) { op.reads({h.host[f]}); op.writes({h.host[f]}); }
   }
-  finish();
+  op.na = 15;
+  h.depth = depth;
+  op.run = [=] { run_exchange(g, h); };
+  submit(std::move(op));
 }
 
 static void allreduce_host(double* values, int n, ncclRedOp_t op) {
   ensure_init();
+  flush_deferred();
   if (!N.comm || N.nranks == 1) return;
   if (n > 16) fatal("allreduce of %d values (max 16)", n);
   CLV_CUDA(cudaMemcpyAsync(N.d_scal, values, n * sizeof(double), cudaMemcpyHostToDevice, stream()));

@@ -16,72 +16,10 @@
 // Stencil neighbours come through L1.  Algorithmic bytes per cell are listed in DESIGN.md.
 #include "clover_b200.h"
 #include "common.cuh"
+#include "lagrange.cuh"
 
 namespace clv {
 
-constexpr int BX = 32, BY = 8;
-// rows per thread, per kernel (tuned on B200, see profiles/)
-constexpr int NR_IDEAL = 4, NR_VISC = 1, NR_DT = 1, NR_PDV = 2, NR_COPY = 4, NR_RESET = 1, NR_ACC = 1, NR_FLUX = 2,
-              NR_SUM = 2;
-
-struct Range {
-  int j0, j1, k0, k1;  // inclusive
-  int jbase;           // first column handled by block x = 0 (16-double aligned)
-};
-
-static inline Range make_range(int j0, int j1, int k0, int k1) {
-  Range r{j0, j1, k0, k1, 0};
-  r.jbase = ((j0 + XOFF) & ~15) - XOFF;
-  return r;
-}
-static inline dim3 grid_for(const Range& r, int nr) {
-  return dim3((unsigned)((r.j1 - r.jbase + 1 + BX - 1) / BX),
-              (unsigned)((r.k1 - r.k0 + 1 + BY * nr - 1) / (BY * nr)), 1);
-}
-// Opens the unrolled row loop: defines j, k (clamped into the range, always safe to load from) and
-// `active` (this thread really owns (j,k): predicate for stores / reductions).
-#define CLV_ROWS_BEGIN(r, NR)                                                          \
-  const int j_raw_ = (r).jbase + (int)(blockIdx.x * BX + threadIdx.x);                 \
-  const bool j_ok_ = (j_raw_ >= (r).j0) && (j_raw_ <= (r).j1);                         \
-  const int j = j_raw_ < (r).j0 ? (r).j0 : (j_raw_ > (r).j1 ? (r).j1 : j_raw_);        \
-  _Pragma("unroll") for (int rr_ = 0; rr_ < (NR); ++rr_) {                             \
-    const int k_raw_ = (r).k0 + (int)((blockIdx.y * (NR) + rr_) * BY + threadIdx.y);   \
-    const bool active = j_ok_ && (k_raw_ <= (r).k1);                                   \
-    const int k = k_raw_ <= (r).k1 ? k_raw_ : (r).k1;
-#define CLV_ROWS_END }
-// Persistent variant for the reduction kernels: a 1-D grid of a few CTAs per SM walks the same 32x(8*NR)
-// tiles in a grid-stride loop, so that the block-level reduction tail (fence + ticket atomic) is paid once
-// per CTA instead of once per tile (it held every warp of a 256-cell block hostage for ~2k cycles).
-#define CLV_PTILES_BEGIN(r, NR)                                                        \
-  const unsigned tiles_x_ = (unsigned)(((r).j1 - (r).jbase + BX) / BX);                \
-  const unsigned tiles_y_ = (unsigned)(((r).k1 - (r).k0 + BY * (NR)) / (BY * (NR)));   \
-  for (unsigned tile_ = blockIdx.x; tile_ < tiles_x_ * tiles_y_; tile_ += gridDim.x) { \
-    const unsigned bx_ = tile_ % tiles_x_, by_ = tile_ / tiles_x_;                     \
-    const int j_raw_ = (r).jbase + (int)(bx_ * BX + threadIdx.x);                      \
-    const bool j_ok_ = (j_raw_ >= (r).j0) && (j_raw_ <= (r).j1);                       \
-    const int j = j_raw_ < (r).j0 ? (r).j0 : (j_raw_ > (r).j1 ? (r).j1 : j_raw_);      \
-    _Pragma("unroll") for (int rr_ = 0; rr_ < (NR); ++rr_) {                           \
-      const int k_raw_ = (r).k0 + (int)((by_ * (NR) + rr_) * BY + threadIdx.y);        \
-      const bool active = j_ok_ && (k_raw_ <= (r).k1);                                 \
-      const int k = k_raw_ <= (r).k1 ? k_raw_ : (r).k1;
-#define CLV_PTILES_END }}
-static inline dim3 persistent_grid(const Range& r, int nr, int ctas_per_sm) {
-  const dim3 g = grid_for(r, nr);
-  const unsigned tiles = g.x * g.y, cap = 148u * (unsigned)ctas_per_sm;
-  return dim3(tiles < cap ? tiles : cap, 1, 1);
-}
-
-// ------------------------------------------------------------------------------------------------
-// ideal_gas_kernel_c.c:48-59.  4 passes (2 reads, 2 writes) = 32 B/cell.
-template <bool SAFE>
-__device__ __forceinline__ void ideal_gas_cell(double rho, double e, double& p, double& ss, bool& bad) {
-  const double v = Math<SAFE>::rcp(rho, bad);
-  p = (1.4 - 1.0) * rho * e;
-  const double pe = (1.4 - 1.0) * rho;
-  const double pv = -rho * p;
-  const double ss2 = v * v * (p * pe - pv);
-  ss = Math<SAFE>::sqrt(ss2, bad);
-}
 template <int NR>
 __global__ void __launch_bounds__(BX* BY)
     ideal_gas_kernel(Range r, int pitch, const double* __restrict__ density,
@@ -115,44 +53,6 @@ __global__ void __launch_bounds__(BX* BY)
       }
     CLV_ROWS_END
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// viscosity_kernel_c.c:53-104.  5 passes = 40 B/cell.
-struct ViscIn {
-  double u00, u10, u01, u11, v00, v10, v01, v11, dx, dy, dx1, dy1, pl, pr, pb, pt, rho;
-};
-template <bool SAFE>
-__device__ __forceinline__ double viscosity_cell(const ViscIn& I, bool& bad) {
-  typedef Math<SAFE> M;
-  const double ugrad = (I.u10 + I.u11) - (I.u00 + I.u01);
-  const double vgrad = (I.v01 + I.v11) - (I.v00 + I.v10);
-  const double div = I.dx * ugrad + I.dy * vgrad;
-  // viscosity_kernel_c.c:88: `if (limiter>0.0 || div>=0.0) viscosity = 0`.  The limiter (7 divisions)
-  // only decides anything for a compressing cell, so it is evaluated only there; everywhere else --
-  // the whole quiescent part of the mesh -- the answer is 0 whatever the limiter is.
-  if (div >= 0.0) return 0.0;
-  const double strain2 = M::div(0.5 * (I.u01 + I.u11 - I.u00 - I.u10), I.dy, bad) +
-                         M::div(0.5 * (I.v10 + I.v11 - I.v00 - I.v01), I.dx, bad);
-  double pgradx = M::div(I.pr - I.pl, I.dx + I.dx1, bad);
-  double pgrady = M::div(I.pt - I.pb, I.dy + I.dy1, bad);
-  const double pgradx2 = pgradx * pgradx, pgrady2 = pgrady * pgrady;
-  const double limiter = M::div(M::div(0.5 * ugrad, I.dx, bad) * pgradx2 + M::div(0.5 * vgrad, I.dy, bad) * pgrady2 +
-                                    strain2 * pgradx * pgrady,
-                                dmax(pgradx2 + pgrady2, 1.0e-16), bad);
-  double q = 0.0;
-  if (!(limiter > 0.0)) {  // generic operators in this minority branch
-    const double ax = dmax(1.0e-16, fabs(pgradx)), ay = dmax(1.0e-16, fabs(pgrady));
-    pgradx = (pgradx < 0.0) ? -ax : ax;
-    pgrady = (pgrady < 0.0) ? -ay : ay;
-    const double pgrad = sqrt(pgradx * pgradx + pgrady * pgrady);
-    const double xgrad = fabs(I.dx * pgrad / pgradx);
-    const double ygrad = fabs(I.dy * pgrad / pgrady);
-    const double grad = dmin(xgrad, ygrad);
-    const double grad2 = grad * grad;
-    q = 2.0 * I.rho * grad2 * limiter * limiter;
-  }
-  return q;
 }
 
 template <int NR>
@@ -194,92 +94,6 @@ __global__ void __launch_bounds__(BX* BY)
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Block-level reduction tails shared by calc_dt and field_summary: every block publishes its
-// partial(s), the last block to arrive (ticket) folds them in a fixed order and writes the result
-// to pinned host memory, then re-arms the ticket.
-template <int N, bool IS_MIN>
-__device__ __forceinline__ void block_reduce_publish(double (&v)[N], double* __restrict__ partials,
-                                                     unsigned int* ticket, double* __restrict__ out,
-                                                     double identity) {
-  __shared__ double sm[N][BX * BY / 32];
-  __shared__ bool last;
-  const int tid = threadIdx.y * BX + threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  const unsigned nblocks = gridDim.x * gridDim.y;
-  const unsigned bid = blockIdx.y * gridDim.x + blockIdx.x;
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    double w = IS_MIN ? warp_min(v[i]) : warp_sum(v[i]);
-    if (lane == 0) sm[i][warp] = w;
-  }
-  __syncthreads();
-  if (tid == 0) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      double a = sm[i][0];
-      for (int w = 1; w < BX * BY / 32; ++w) a = IS_MIN ? ((sm[i][w] < a) ? sm[i][w] : a) : a + sm[i][w];
-      partials[(size_t)i * nblocks + bid] = a;
-    }
-    __threadfence();
-    const unsigned t = atomicAdd(ticket, 1u);
-    last = (t == nblocks - 1);
-  }
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    double a = identity;
-    for (unsigned b = tid; b < nblocks; b += BX * BY) {
-      const double p = __ldcg(&partials[(size_t)i * nblocks + b]);
-      a = IS_MIN ? ((p < a) ? p : a) : a + p;
-    }
-    a = IS_MIN ? warp_min(a) : warp_sum(a);
-    if (lane == 0) sm[i][warp] = a;
-  }
-  __syncthreads();
-  if (tid == 0) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      double a = sm[i][0];
-      for (int w = 1; w < BX * BY / 32; ++w) a = IS_MIN ? ((sm[i][w] < a) ? sm[i][w] : a) : a + sm[i][w];
-      out[i] = a;
-    }
-    *ticket = 0;
-    __threadfence_system();
-  }
-}
-
-// calc_dt_kernel_c.c:96-144.  8 passes read = 64 B/cell; no per-cell dt_min array is written.
-struct DtParams {
-  double g_small, g_big, dtc_safe, dtu_safe, dtv_safe, dtdiv_safe;
-};
-struct DtIn {
-  double dsx, dsy, vol, ssp, visc, rho, u00, u10, u01, u11, v00, v10, v01, v11, xa0, xa1, ya0, ya1;
-};
-// calc_dt_kernel_c.c:99-133, one cell.  The sqrt and the four divisions are independent chains.
-template <bool SAFE>
-__device__ __forceinline__ double calc_dt_cell(const DtIn& I, const DtParams& P, bool& bad) {
-  typedef Math<SAFE> M;
-  double cc = I.ssp * I.ssp;
-  cc = cc + M::div(2.0 * I.visc, I.rho, bad);
-  cc = dmax(M::sqrt(cc, bad), P.g_small);
-  const double dtct = M::div(P.dtc_safe * dmin(I.dsx, I.dsy), cc, bad);
-  double div = 0.0;
-  double dv1 = (I.u00 + I.u01) * I.xa0;
-  double dv2 = (I.u10 + I.u11) * I.xa1;
-  div = div + dv2 - dv1;
-  const double dtut = M::div(P.dtu_safe * 2.0 * I.vol, dmax(fabs(dv1), dmax(fabs(dv2), P.g_small * I.vol)), bad);
-  dv1 = (I.v00 + I.v10) * I.ya0;
-  dv2 = (I.v01 + I.v11) * I.ya1;
-  div = div + dv2 - dv1;
-  const double dtvt = M::div(P.dtv_safe * 2.0 * I.vol, dmax(fabs(dv1), dmax(fabs(dv2), P.g_small * I.vol)), bad);
-  div = M::div(div, 2.0 * I.vol, bad);
-  // the divergence limit applies to compressing cells only: generic operator in that minority branch
-  const double dtdivt = (div < -P.g_small) ? P.dtdiv_safe * (-1.0 / div) : P.g_big;
-  return dmin(dtct, dmin(dtut, dmin(dtvt, dtdivt)));
-}
 template <int NR>
 __global__ void __launch_bounds__(BX* BY)
     calc_dt_kernel(Range r, int pitch, DtParams P, const double* __restrict__ xarea,
@@ -495,31 +309,60 @@ __global__ void __launch_bounds__(BX* BY)
   CLV_ROWS_END
 }
 
-}  // namespace clv
+// reset_field as a buffer swap: after the device buffers of (x0, x1) have been exchanged, the cells OUTSIDE
+// the update range (the halo rings, which reset_field_kernel_c.c:46-76 does not touch) are swapped back so
+// that both arrays keep their own halos.  One launch for the four pairs.
+struct RingPairs {
+  double* a[4];
+  double* b[4];
+  int ext[4];  // 0 cell data (update range 1..nx x 1..ny), 1 vertex data (1..nx+1 x 1..ny+1)
+};
+__global__ void __launch_bounds__(256) ring_swap_kernel(RingPairs P, int nx, int ny, int pitch) {
+  const int e = P.ext[blockIdx.y];
+  const int W = nx + 4 + e, H = ny + 4 + e;        // Fortran extent (-1..nx+2+e) x (-1..ny+2+e)
+  const int n_bt = 4 * W, n_lr = 4 * (H - 4);      // two full rows below + above, two columns left + right
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_bt + n_lr) return;
+  int j, k;
+  if (t < n_bt) {
+    const int r = t / W;
+    j = -1 + t % W;
+    k = r < 2 ? -1 + r : ny + e + (r - 1);
+  } else {
+    const int u = t - n_bt, c = u / (H - 4);
+    k = 1 + u % (H - 4);
+    j = c < 2 ? -1 + c : nx + e + (c - 1);
+  }
+  const size_t i = idx2(pitch, j, k);
+  double* __restrict__ a = P.a[blockIdx.y];
+  double* __restrict__ b = P.b[blockIdx.y];
+  const double va = a[i], vb = b[i];
+  a[i] = vb;
+  b[i] = va;
+}
 
-using namespace clv;
+// copy of one array's update range (materialisation of a lazy copy, runtime.cu)
+void launch_copy_range(const Grid& g, const double* src, double* dst, Kind kind) {
+  const int e = (kind == VERTEX) ? 1 : 0;
+  if (kind != CELL && kind != VERTEX) fatal("lazy copy of a non cell/vertex array");
+  const Range r = make_range(1, g.nx + e, 1, g.ny + e);
+  LaunchScope ls("lazy_copy");
+  copy2_kernel<NR_COPY><<<grid_for(r, NR_COPY), dim3(BX, BY), 0, stream()>>>(r, g.pitch, src, dst, src, dst);
+}
 
-extern "C" {
-
-void ideal_gas_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* density, double* energy,
-                         double* pressure, double* soundspeed) {
-  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+// ---- the calls on their own (host side): look up the device mirrors, launch ---------------------------
+void run_ideal_gas(const Grid& g, double* density, double* energy, double* pressure, double* soundspeed) {
   const double* d = dev(g, density, CELL, IN);
   const double* e = dev(g, energy, CELL, IN);
   double* p = dev(g, pressure, CELL, OUT);
   double* ss = dev(g, soundspeed, CELL, OUT);
   const Range r = make_range(1, g.nx, 1, g.ny);
-  {
-    LaunchScope ls("ideal_gas");
-    ideal_gas_kernel<NR_IDEAL><<<grid_for(r, NR_IDEAL), dim3(BX, BY), 0, stream()>>>(r, g.pitch, d, e, p, ss);
-  }
-  finish();
+  LaunchScope ls("ideal_gas");
+  ideal_gas_kernel<NR_IDEAL><<<grid_for(r, NR_IDEAL), dim3(BX, BY), 0, stream()>>>(r, g.pitch, d, e, p, ss);
 }
 
-void viscosity_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* celldx, double* celldy,
-                         double* density0, double* pressure, double* viscosity, double* xvel0,
-                         double* yvel0) {
-  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+void run_viscosity(const Grid& g, double* celldx, double* celldy, double* density0, double* pressure,
+                   double* viscosity, double* xvel0, double* yvel0) {
   const double* cdx = dev(g, celldx, X1D_CELL, IN);
   const double* cdy = dev(g, celldy, Y1D_CELL, IN);
   const double* d0 = dev(g, density0, CELL, IN);
@@ -528,24 +371,14 @@ void viscosity_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* cel
   const double* xv = dev(g, xvel0, VERTEX, IN);
   const double* yv = dev(g, yvel0, VERTEX, IN);
   const Range r = make_range(1, g.nx, 1, g.ny);
-  {
-    LaunchScope ls("viscosity");
-    viscosity_kernel<NR_VISC><<<grid_for(r, NR_VISC), dim3(BX, BY), 0, stream()>>>(r, g.pitch, cdx, cdy, d0, p, q,
-                                                                                 xv, yv);
-  }
-  finish();
+  LaunchScope ls("viscosity");
+  viscosity_kernel<NR_VISC><<<grid_for(r, NR_VISC), dim3(BX, BY), 0, stream()>>>(r, g.pitch, cdx, cdy, d0, p, q, xv, yv);
 }
 
-void calc_dt_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* g_small, double* g_big,
-                       double* dtmin, double* dtc_safe, double* dtu_safe, double* dtv_safe,
-                       double* dtdiv_safe, double* xarea, double* yarea, double* cellx, double* celly,
-                       double* celldx, double* celldy, double* volume, double* density0,
-                       double* energy0, double* pressure, double* viscosity, double* soundspeed,
-                       double* xvel0, double* yvel0, double* dt_min, double* dt_min_val,
-                       int* dtl_control, double* xl_pos, double* yl_pos, int* jldt, int* kldt,
-                       int* small) {
-  (void)cellx; (void)celly; (void)energy0; (void)pressure; (void)dt_min; (void)xl_pos; (void)yl_pos;
-  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+// the result lands in host_scalars()[0] once the stream has drained
+void run_calc_dt(const Grid& g, const DtParams& P, double* xarea, double* yarea, double* celldx, double* celldy,
+                 double* volume, double* density0, double* viscosity, double* soundspeed, double* xvel0,
+                 double* yvel0) {
   const double* xa = dev(g, xarea, XFACE, IN);
   const double* ya = dev(g, yarea, YFACE, IN);
   const double* cdx = dev(g, celldx, X1D_CELL, IN);
@@ -559,40 +392,21 @@ void calc_dt_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* g_sma
   const Range r = make_range(1, g.nx, 1, g.ny);
   const dim3 grid = persistent_grid(r, NR_DT, 6);
   double* part = partials((size_t)grid.x * grid.y);
-  DtParams P{*g_small, *g_big, *dtc_safe, *dtu_safe, *dtv_safe, *dtdiv_safe};
-  double* out = host_scalars();
-  {
-    LaunchScope ls("calc_dt");
-    calc_dt_kernel<NR_DT><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, P, xa, ya, cdx, cdy, vol, d0, q, ss, xv,
-                                                               yv, part, ticket(), out);
-  }
-  CLV_CUDA(cudaStreamSynchronize(stream()));  // the one unavoidable host-visible result per step
-  const double v = out[0];
-  *dt_min_val = v;
-  *dtl_control = 1;  // calc_dt_kernel_c.c:159-163
-  *jldt = 1;
-  *kldt = 1;
-  if (v < *dtmin) {
-    if (small) *small = 1;
-    printf("Timestep information:\ntimestep : %f (below dtmin)\n", v);
-  }
-  finish();
+  LaunchScope ls("calc_dt");
+  calc_dt_kernel<NR_DT><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, P, xa, ya, cdx, cdy, vol, d0, q, ss, xv, yv,
+                                                             part, ticket(), host_scalars());
 }
 
-void pdv_kernel_c_(int* prdct, int* xmin, int* xmax, int* ymin, int* ymax, double* dt, double* xarea,
-                   double* yarea, double* volume, double* density0, double* density1, double* energy0,
-                   double* energy1, double* pressure, double* viscosity, double* xvel0, double* xvel1,
-                   double* yvel0, double* yvel1, double* volume_change) {
-  (void)volume_change;
-  const Grid g = grid_of(xmin, xmax, ymin, ymax);
-  const bool predict = (*prdct == 0);
+void run_pdv(const Grid& g, bool predict, double dt, double* xarea, double* yarea, double* volume, double* density0,
+             double* density1, double* energy0, double* energy1, double* pressure, double* viscosity,
+             double* xvel0, double* xvel1, double* yvel0, double* yvel1) {
   const double* xa = dev(g, xarea, XFACE, IN);
   const double* ya = dev(g, yarea, YFACE, IN);
   const double* vol = dev(g, volume, CELL, IN);
   const double* d0 = dev(g, density0, CELL, IN);
-  double* d1 = dev(g, density1, CELL, OUT);
+  double* d1 = dev(g, density1, CELL, OUT_FULL);
   const double* e0 = dev(g, energy0, CELL, IN);
-  double* e1 = dev(g, energy1, CELL, OUT);
+  double* e1 = dev(g, energy1, CELL, OUT_FULL);
   const double* p = dev(g, pressure, CELL, IN);
   const double* q = dev(g, viscosity, CELL, IN);
   const double* x0 = dev(g, xvel0, VERTEX, IN);
@@ -601,37 +415,57 @@ void pdv_kernel_c_(int* prdct, int* xmin, int* xmax, int* ymin, int* ymax, doubl
   const dim3 grid = grid_for(r, NR_PDV);
   if (predict) {
     LaunchScope ls("pdv_predict");
-    pdv_kernel<true, NR_PDV><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, *dt, xa, ya, vol, d0, d1, e0, e1, p, q,
-                                                                  x0, x0, y0, y0);
+    pdv_kernel<true, NR_PDV><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, dt, xa, ya, vol, d0, d1, e0, e1, p, q, x0,
+                                                                  x0, y0, y0);
   } else {
     const double* x1 = dev(g, xvel1, VERTEX, IN);
     const double* y1 = dev(g, yvel1, VERTEX, IN);
     LaunchScope ls("pdv_correct");
-    pdv_kernel<false, NR_PDV><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, *dt, xa, ya, vol, d0, d1, e0, e1, p,
-                                                                   q, x0, x1, y0, y1);
+    pdv_kernel<false, NR_PDV><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, dt, xa, ya, vol, d0, d1, e0, e1, p, q,
+                                                                   x0, x1, y0, y1);
   }
-  finish();
 }
 
-void revert_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* density0, double* density1,
-                      double* energy0, double* energy1) {
-  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+void run_revert(const Grid& g, double* density0, double* density1, double* energy0, double* energy1) {
+  if (is_resident()) {  // recorded, not copied: the corrector overwrites both before anything reads them
+    lazy_copy(g, density1, density0, CELL);
+    lazy_copy(g, energy1, energy0, CELL);
+    return;
+  }
   const double* d0 = dev(g, density0, CELL, IN);
   double* d1 = dev(g, density1, CELL, OUT);
   const double* e0 = dev(g, energy0, CELL, IN);
   double* e1 = dev(g, energy1, CELL, OUT);
   const Range r = make_range(1, g.nx, 1, g.ny);
-  {
-    LaunchScope ls("revert");
-    copy2_kernel<NR_COPY><<<grid_for(r, NR_COPY), dim3(BX, BY), 0, stream()>>>(r, g.pitch, d0, d1, e0, e1);
-  }
-  finish();
+  LaunchScope ls("revert");
+  copy2_kernel<NR_COPY><<<grid_for(r, NR_COPY), dim3(BX, BY), 0, stream()>>>(r, g.pitch, d0, d1, e0, e1);
 }
 
-void reset_field_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* density0,
-                           double* density1, double* energy0, double* energy1, double* xvel0,
-                           double* xvel1, double* yvel0, double* yvel1) {
-  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+void run_reset_field(const Grid& g, double* density0, double* density1, double* energy0, double* energy1,
+                     double* xvel0, double* xvel1, double* yvel0, double* yvel1) {
+  if (is_resident()) {
+    // x0 := x1 on the update range.  Swap the two device buffers, swap the halo rings back, and record
+    // "x1 := x0" as a lazy copy (the next PdV / accelerate overwrites x1 before anything reads it).
+    double* h0[4] = {density0, energy0, xvel0, yvel0};
+    double* h1[4] = {density1, energy1, xvel1, yvel1};
+    const Kind kinds[4] = {CELL, CELL, VERTEX, VERTEX};
+    RingPairs P;
+    for (int i = 0; i < 4; ++i) {
+      dev(g, h1[i], kinds[i], IN);     // the source really holds its data
+      dev(g, h0[i], kinds[i], INOUT);  // nothing pending on or from the destination
+      swap_buffers(h0[i], h1[i]);
+      P.a[i] = dev(g, h0[i], kinds[i], INOUT);
+      P.b[i] = dev(g, h1[i], kinds[i], INOUT);
+      P.ext[i] = kinds[i] == VERTEX ? 1 : 0;
+    }
+    {
+      const int ring = 4 * (g.nx + 5) + 4 * (g.ny + 1);
+      LaunchScope ls("reset_field_swap");
+      ring_swap_kernel<<<dim3((unsigned)((ring + 255) / 256), 4), 256, 0, stream()>>>(P, g.nx, g.ny, g.pitch);
+    }
+    for (int i = 0; i < 4; ++i) lazy_copy(g, h1[i], h0[i], kinds[i]);
+    return;
+  }
   double* d0 = dev(g, density0, CELL, OUT);
   const double* d1 = dev(g, density1, CELL, IN);
   double* e0 = dev(g, energy0, CELL, OUT);
@@ -641,19 +475,14 @@ void reset_field_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* d
   double* y0 = dev(g, yvel0, VERTEX, OUT);
   const double* y1 = dev(g, yvel1, VERTEX, IN);
   const Range r = make_range(1, g.nx + 1, 1, g.ny + 1);
-  {
-    LaunchScope ls("reset_field");
-    reset_field_kernel<NR_RESET><<<grid_for(r, NR_RESET), dim3(BX, BY), 0, stream()>>>(r, g.pitch, g.nx, g.ny, d0, d1,
-                                                                                    e0, e1, x0, x1, y0, y1);
-  }
-  finish();
+  LaunchScope ls("reset_field");
+  reset_field_kernel<NR_RESET><<<grid_for(r, NR_RESET), dim3(BX, BY), 0, stream()>>>(r, g.pitch, g.nx, g.ny, d0, d1, e0,
+                                                                                  e1, x0, x1, y0, y1);
 }
 
-void accelerate_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* dt, double* xarea,
-                          double* yarea, double* volume, double* density0, double* pressure,
-                          double* viscosity, double* xvel0, double* yvel0, double* xvel1,
-                          double* yvel1) {
-  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+void run_accelerate(const Grid& g, double dt, double* xarea, double* yarea, double* volume, double* density0,
+                    double* pressure, double* viscosity, double* xvel0, double* yvel0, double* xvel1,
+                    double* yvel1) {
   const double* xa = dev(g, xarea, XFACE, IN);
   const double* ya = dev(g, yarea, YFACE, IN);
   const double* vol = dev(g, volume, CELL, IN);
@@ -662,21 +491,16 @@ void accelerate_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* dt
   const double* q = dev(g, viscosity, CELL, IN);
   const double* x0 = dev(g, xvel0, VERTEX, IN);
   const double* y0 = dev(g, yvel0, VERTEX, IN);
-  double* x1 = dev(g, xvel1, VERTEX, OUT);
-  double* y1 = dev(g, yvel1, VERTEX, OUT);
+  double* x1 = dev(g, xvel1, VERTEX, OUT_FULL);
+  double* y1 = dev(g, yvel1, VERTEX, OUT_FULL);
   const Range r = make_range(1, g.nx + 1, 1, g.ny + 1);
-  {
-    LaunchScope ls("accelerate");
-    accelerate_kernel<NR_ACC><<<grid_for(r, NR_ACC), dim3(BX, BY), 0, stream()>>>(r, g.pitch, *dt, xa, ya, vol, d0, p,
-                                                                                q, x0, y0, x1, y1);
-  }
-  finish();
+  LaunchScope ls("accelerate");
+  accelerate_kernel<NR_ACC><<<grid_for(r, NR_ACC), dim3(BX, BY), 0, stream()>>>(r, g.pitch, dt, xa, ya, vol, d0, p, q,
+                                                                              x0, y0, x1, y1);
 }
 
-void flux_calc_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* dt, double* xarea,
-                         double* yarea, double* xvel0, double* yvel0, double* xvel1, double* yvel1,
-                         double* vol_flux_x, double* vol_flux_y) {
-  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+void run_flux_calc(const Grid& g, double dt, double* xarea, double* yarea, double* xvel0, double* yvel0,
+                   double* xvel1, double* yvel1, double* vol_flux_x, double* vol_flux_y) {
   const double* xa = dev(g, xarea, XFACE, IN);
   const double* ya = dev(g, yarea, YFACE, IN);
   const double* x0 = dev(g, xvel0, VERTEX, IN);
@@ -686,19 +510,172 @@ void flux_calc_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* dt,
   double* fx = dev(g, vol_flux_x, XFACE, OUT);
   double* fy = dev(g, vol_flux_y, YFACE, OUT);
   const Range r = make_range(1, g.nx + 1, 1, g.ny + 1);
-  {
-    LaunchScope ls("flux_calc");
-    flux_calc_kernel<NR_FLUX><<<grid_for(r, NR_FLUX), dim3(BX, BY), 0, stream()>>>(r, g.pitch, g.nx, g.ny, *dt, xa, ya,
-                                                                                 x0, y0, x1, y1, fx, fy);
+  LaunchScope ls("flux_calc");
+  flux_calc_kernel<NR_FLUX><<<grid_for(r, NR_FLUX), dim3(BX, BY), 0, stream()>>>(r, g.pitch, g.nx, g.ny, dt, xa, ya, x0,
+                                                                               y0, x1, y1, fx, fy);
+}
+
+}  // namespace clv
+
+using namespace clv;
+
+extern "C" {
+
+// Op::a = {density, energy, pressure, soundspeed}
+void ideal_gas_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* density, double* energy,
+                         double* pressure, double* soundspeed) {
+  Op op;
+  op.kind = OP_IDEAL_GAS;
+  const Grid g = op.g = grid_of_noflush(xmin, xmax, ymin, ymax);
+  double* a[] = {density, energy, pressure, soundspeed};
+  for (double* p : a) op.a[op.na++] = p;
+  op.reads({density, energy});
+  op.overwrites({pressure, soundspeed});
+  op.run = [=] { run_ideal_gas(g, density, energy, pressure, soundspeed); };
+  submit(std::move(op));
+}
+
+// Op::a = {celldx, celldy, density0, pressure, viscosity, xvel0, yvel0}
+void viscosity_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* celldx, double* celldy,
+                         double* density0, double* pressure, double* viscosity, double* xvel0,
+                         double* yvel0) {
+  Op op;
+  op.kind = OP_VISCOSITY;
+  const Grid g = op.g = grid_of_noflush(xmin, xmax, ymin, ymax);
+  double* a[] = {celldx, celldy, density0, pressure, viscosity, xvel0, yvel0};
+  for (double* p : a) op.a[op.na++] = p;
+  op.reads({celldx, celldy, density0, pressure, xvel0, yvel0});
+  op.overwrites({viscosity});
+  op.run = [=] { run_viscosity(g, celldx, celldy, density0, pressure, viscosity, xvel0, yvel0); };
+  submit(std::move(op));
+}
+
+// Op::a = {xarea, yarea, celldx, celldy, volume, density0, viscosity, soundspeed, xvel0, yvel0}; sv = DtParams
+void calc_dt_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* g_small, double* g_big,
+                       double* dtmin, double* dtc_safe, double* dtu_safe, double* dtv_safe,
+                       double* dtdiv_safe, double* xarea, double* yarea, double* cellx, double* celly,
+                       double* celldx, double* celldy, double* volume, double* density0,
+                       double* energy0, double* pressure, double* viscosity, double* soundspeed,
+                       double* xvel0, double* yvel0, double* dt_min, double* dt_min_val,
+                       int* dtl_control, double* xl_pos, double* yl_pos, int* jldt, int* kldt,
+                       int* small) {
+  (void)cellx; (void)celly; (void)energy0; (void)pressure; (void)dt_min; (void)xl_pos; (void)yl_pos;
+  Op op;
+  op.kind = OP_CALC_DT;
+  const Grid g = op.g = grid_of_noflush(xmin, xmax, ymin, ymax);
+  double* a[] = {xarea, yarea, celldx, celldy, volume, density0, viscosity, soundspeed, xvel0, yvel0};
+  for (double* p : a) op.a[op.na++] = p;
+  const DtParams P{*g_small, *g_big, *dtc_safe, *dtu_safe, *dtv_safe, *dtdiv_safe};
+  op.sv[0] = P.g_small; op.sv[1] = P.g_big; op.sv[2] = P.dtc_safe; op.sv[3] = P.dtu_safe; op.sv[4] = P.dtv_safe;
+  op.sv[5] = P.dtdiv_safe;
+  op.reads({xarea, yarea, celldx, celldy, volume, density0, viscosity, soundspeed, xvel0, yvel0});
+  op.run = [=] { run_calc_dt(g, P, xarea, yarea, celldx, celldy, volume, density0, viscosity, soundspeed, xvel0, yvel0); };
+  submit(std::move(op));
+  flush_deferred();
+  CLV_CUDA(cudaStreamSynchronize(stream()));  // the one unavoidable host-visible result per step
+  const double v = host_scalars()[0];
+  *dt_min_val = v;
+  *dtl_control = 1;  // calc_dt_kernel_c.c:159-163
+  *jldt = 1;
+  *kldt = 1;
+  if (v < *dtmin) {
+    if (small) *small = 1;
+    printf("Timestep information:\ntimestep : %f (below dtmin)\n", v);
   }
-  finish();
+}
+
+// Op::a = {xarea, yarea, volume, density0, density1, energy0, energy1, pressure, viscosity, xvel0, xvel1, yvel0,
+//          yvel1}; sv[0] = dt
+void pdv_kernel_c_(int* prdct, int* xmin, int* xmax, int* ymin, int* ymax, double* dt, double* xarea,
+                   double* yarea, double* volume, double* density0, double* density1, double* energy0,
+                   double* energy1, double* pressure, double* viscosity, double* xvel0, double* xvel1,
+                   double* yvel0, double* yvel1, double* volume_change) {
+  (void)volume_change;
+  Op op;
+  const bool predict = (*prdct == 0);
+  op.kind = predict ? OP_PDV_PREDICT : OP_PDV_CORRECT;
+  const Grid g = op.g = grid_of_noflush(xmin, xmax, ymin, ymax);
+  double* a[] = {xarea, yarea, volume, density0, density1, energy0, energy1, pressure, viscosity, xvel0, xvel1,
+                 yvel0, yvel1};
+  for (double* p : a) op.a[op.na++] = p;
+  const double dtv = op.sv[0] = *dt;
+  op.reads({xarea, yarea, volume, density0, energy0, pressure, viscosity, xvel0, yvel0});
+  if (!predict) op.reads({xvel1, yvel1});
+  op.overwrites({density1, energy1});
+  op.run = [=] {
+    run_pdv(g, predict, dtv, xarea, yarea, volume, density0, density1, energy0, energy1, pressure, viscosity, xvel0,
+            xvel1, yvel0, yvel1);
+  };
+  submit(std::move(op));
+}
+
+// Op::a = {density0, density1, energy0, energy1}
+void revert_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* density0, double* density1,
+                      double* energy0, double* energy1) {
+  Op op;
+  op.kind = OP_REVERT;
+  const Grid g = op.g = grid_of_noflush(xmin, xmax, ymin, ymax);
+  double* a[] = {density0, density1, energy0, energy1};
+  for (double* p : a) op.a[op.na++] = p;
+  op.reads({density0, energy0});
+  op.overwrites({density1, energy1});
+  op.run = [=] { run_revert(g, density0, density1, energy0, energy1); };
+  submit(std::move(op));
+}
+
+// Op::a = {density0, density1, energy0, energy1, xvel0, xvel1, yvel0, yvel1}
+void reset_field_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* density0,
+                           double* density1, double* energy0, double* energy1, double* xvel0,
+                           double* xvel1, double* yvel0, double* yvel1) {
+  Op op;
+  op.kind = OP_RESET_FIELD;
+  const Grid g = op.g = grid_of_noflush(xmin, xmax, ymin, ymax);
+  double* a[] = {density0, density1, energy0, energy1, xvel0, xvel1, yvel0, yvel1};
+  for (double* p : a) op.a[op.na++] = p;
+  op.reads({density1, energy1, xvel1, yvel1});
+  op.overwrites({density0, energy0, xvel0, yvel0});
+  op.run = [=] { run_reset_field(g, density0, density1, energy0, energy1, xvel0, xvel1, yvel0, yvel1); };
+  submit(std::move(op));
+}
+
+// Op::a = {xarea, yarea, volume, density0, pressure, viscosity, xvel0, yvel0, xvel1, yvel1}; sv[0] = dt
+void accelerate_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* dt, double* xarea,
+                          double* yarea, double* volume, double* density0, double* pressure,
+                          double* viscosity, double* xvel0, double* yvel0, double* xvel1,
+                          double* yvel1) {
+  Op op;
+  op.kind = OP_ACCELERATE;
+  const Grid g = op.g = grid_of_noflush(xmin, xmax, ymin, ymax);
+  double* a[] = {xarea, yarea, volume, density0, pressure, viscosity, xvel0, yvel0, xvel1, yvel1};
+  for (double* p : a) op.a[op.na++] = p;
+  const double dtv = op.sv[0] = *dt;
+  op.reads({xarea, yarea, volume, density0, pressure, viscosity, xvel0, yvel0});
+  op.overwrites({xvel1, yvel1});
+  op.run = [=] { run_accelerate(g, dtv, xarea, yarea, volume, density0, pressure, viscosity, xvel0, yvel0, xvel1, yvel1); };
+  submit(std::move(op));
+}
+
+// Op::a = {xarea, yarea, xvel0, yvel0, xvel1, yvel1, vol_flux_x, vol_flux_y}; sv[0] = dt
+void flux_calc_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* dt, double* xarea,
+                         double* yarea, double* xvel0, double* yvel0, double* xvel1, double* yvel1,
+                         double* vol_flux_x, double* vol_flux_y) {
+  Op op;
+  op.kind = OP_FLUX_CALC;
+  const Grid g = op.g = grid_of_noflush(xmin, xmax, ymin, ymax);
+  double* a[] = {xarea, yarea, xvel0, yvel0, xvel1, yvel1, vol_flux_x, vol_flux_y};
+  for (double* p : a) op.a[op.na++] = p;
+  const double dtv = op.sv[0] = *dt;
+  op.reads({xarea, yarea, xvel0, yvel0, xvel1, yvel1});
+  op.writes({vol_flux_x, vol_flux_y});
+  op.run = [=] { run_flux_calc(g, dtv, xarea, yarea, xvel0, yvel0, xvel1, yvel1, vol_flux_x, vol_flux_y); };
+  submit(std::move(op));
 }
 
 void field_summary_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* volume,
                              double* density0, double* energy0, double* pressure, double* xvel0,
                              double* yvel0, double* vol, double* mass, double* ie, double* ke,
                              double* press) {
-  const Grid g = grid_of(xmin, xmax, ymin, ymax);
+  const Grid g = grid_of(xmin, xmax, ymin, ymax);  // drains the queue
   const double* v = dev(g, volume, CELL, IN);
   const double* d0 = dev(g, density0, CELL, IN);
   const double* e0 = dev(g, energy0, CELL, IN);

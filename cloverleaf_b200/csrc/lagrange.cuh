@@ -1,0 +1,199 @@
+// lagrange.cuh -- device-side building blocks shared by lagrange.cu (one kernel per reference call) and
+// fuse.cu (several reference calls in one kernel): tile/row mapping macros, the per-cell arithmetic of
+// ideal_gas, viscosity and calc_dt in the reference's evaluation order, and the block-reduction tail.
+#pragma once
+#include "common.cuh"
+
+namespace clv {
+
+constexpr int BX = 32, BY = 8;
+// rows per thread, per kernel (tuned on B200, see profiles/)
+constexpr int NR_IDEAL = 4, NR_VISC = 1, NR_DT = 1, NR_PDV = 2, NR_COPY = 4, NR_RESET = 1, NR_ACC = 1, NR_FLUX = 2,
+              NR_SUM = 2;
+
+struct Range {
+  int j0, j1, k0, k1;  // inclusive
+  int jbase;           // first column handled by block x = 0 (16-double aligned)
+};
+
+static inline Range make_range(int j0, int j1, int k0, int k1) {
+  Range r{j0, j1, k0, k1, 0};
+  r.jbase = ((j0 + XOFF) & ~15) - XOFF;
+  return r;
+}
+static inline dim3 grid_for(const Range& r, int nr) {
+  return dim3((unsigned)((r.j1 - r.jbase + 1 + BX - 1) / BX),
+              (unsigned)((r.k1 - r.k0 + 1 + BY * nr - 1) / (BY * nr)), 1);
+}
+// Opens the unrolled row loop: defines j, k (clamped into the range, always safe to load from) and
+// `active` (this thread really owns (j,k): predicate for stores / reductions).
+#define CLV_ROWS_BEGIN(r, NR)                                                          \
+  const int j_raw_ = (r).jbase + (int)(blockIdx.x * BX + threadIdx.x);                 \
+  const bool j_ok_ = (j_raw_ >= (r).j0) && (j_raw_ <= (r).j1);                         \
+  const int j = j_raw_ < (r).j0 ? (r).j0 : (j_raw_ > (r).j1 ? (r).j1 : j_raw_);        \
+  _Pragma("unroll") for (int rr_ = 0; rr_ < (NR); ++rr_) {                             \
+    const int k_raw_ = (r).k0 + (int)((blockIdx.y * (NR) + rr_) * BY + threadIdx.y);   \
+    const bool active = j_ok_ && (k_raw_ <= (r).k1);                                   \
+    const int k = k_raw_ <= (r).k1 ? k_raw_ : (r).k1;
+#define CLV_ROWS_END }
+// Persistent variant for the reduction kernels: a 1-D grid of a few CTAs per SM walks the same 32x(8*NR)
+// tiles in a grid-stride loop, so that the block-level reduction tail (fence + ticket atomic) is paid once
+// per CTA instead of once per tile (it held every warp of a 256-cell block hostage for ~2k cycles).
+#define CLV_PTILES_BEGIN(r, NR)                                                        \
+  const unsigned tiles_x_ = (unsigned)(((r).j1 - (r).jbase + BX) / BX);                \
+  const unsigned tiles_y_ = (unsigned)(((r).k1 - (r).k0 + BY * (NR)) / (BY * (NR)));   \
+  for (unsigned tile_ = blockIdx.x; tile_ < tiles_x_ * tiles_y_; tile_ += gridDim.x) { \
+    const unsigned bx_ = tile_ % tiles_x_, by_ = tile_ / tiles_x_;                     \
+    const int j_raw_ = (r).jbase + (int)(bx_ * BX + threadIdx.x);                      \
+    const bool j_ok_ = (j_raw_ >= (r).j0) && (j_raw_ <= (r).j1);                       \
+    const int j = j_raw_ < (r).j0 ? (r).j0 : (j_raw_ > (r).j1 ? (r).j1 : j_raw_);      \
+    _Pragma("unroll") for (int rr_ = 0; rr_ < (NR); ++rr_) {                           \
+      const int k_raw_ = (r).k0 + (int)((by_ * (NR) + rr_) * BY + threadIdx.y);        \
+      const bool active = j_ok_ && (k_raw_ <= (r).k1);                                 \
+      const int k = k_raw_ <= (r).k1 ? k_raw_ : (r).k1;
+#define CLV_PTILES_END }}
+static inline dim3 persistent_grid(const Range& r, int nr, int ctas_per_sm) {
+  const dim3 g = grid_for(r, nr);
+  const unsigned tiles = g.x * g.y, cap = 148u * (unsigned)ctas_per_sm;
+  return dim3(tiles < cap ? tiles : cap, 1, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ideal_gas_kernel_c.c:48-59.  4 passes (2 reads, 2 writes) = 32 B/cell.
+template <bool SAFE>
+__device__ __forceinline__ void ideal_gas_cell(double rho, double e, double& p, double& ss, bool& bad) {
+  const double v = Math<SAFE>::rcp(rho, bad);
+  p = (1.4 - 1.0) * rho * e;
+  const double pe = (1.4 - 1.0) * rho;
+  const double pv = -rho * p;
+  const double ss2 = v * v * (p * pe - pv);
+  ss = Math<SAFE>::sqrt(ss2, bad);
+}
+
+// ------------------------------------------------------------------------------------------------
+// viscosity_kernel_c.c:53-104.  5 passes = 40 B/cell.
+struct ViscIn {
+  double u00, u10, u01, u11, v00, v10, v01, v11, dx, dy, dx1, dy1, pl, pr, pb, pt, rho;
+};
+template <bool SAFE>
+__device__ __forceinline__ double viscosity_cell(const ViscIn& I, bool& bad) {
+  typedef Math<SAFE> M;
+  const double ugrad = (I.u10 + I.u11) - (I.u00 + I.u01);
+  const double vgrad = (I.v01 + I.v11) - (I.v00 + I.v10);
+  const double div = I.dx * ugrad + I.dy * vgrad;
+  // viscosity_kernel_c.c:88: `if (limiter>0.0 || div>=0.0) viscosity = 0`.  The limiter (7 divisions)
+  // only decides anything for a compressing cell, so it is evaluated only there; everywhere else --
+  // the whole quiescent part of the mesh -- the answer is 0 whatever the limiter is.
+  if (div >= 0.0) return 0.0;
+  const double strain2 = M::div(0.5 * (I.u01 + I.u11 - I.u00 - I.u10), I.dy, bad) +
+                         M::div(0.5 * (I.v10 + I.v11 - I.v00 - I.v01), I.dx, bad);
+  double pgradx = M::div(I.pr - I.pl, I.dx + I.dx1, bad);
+  double pgrady = M::div(I.pt - I.pb, I.dy + I.dy1, bad);
+  const double pgradx2 = pgradx * pgradx, pgrady2 = pgrady * pgrady;
+  const double limiter = M::div(M::div(0.5 * ugrad, I.dx, bad) * pgradx2 + M::div(0.5 * vgrad, I.dy, bad) * pgrady2 +
+                                    strain2 * pgradx * pgrady,
+                                dmax(pgradx2 + pgrady2, 1.0e-16), bad);
+  double q = 0.0;
+  if (!(limiter > 0.0)) {  // generic operators in this minority branch
+    const double ax = dmax(1.0e-16, fabs(pgradx)), ay = dmax(1.0e-16, fabs(pgrady));
+    pgradx = (pgradx < 0.0) ? -ax : ax;
+    pgrady = (pgrady < 0.0) ? -ay : ay;
+    const double pgrad = sqrt(pgradx * pgradx + pgrady * pgrady);
+    const double xgrad = fabs(I.dx * pgrad / pgradx);
+    const double ygrad = fabs(I.dy * pgrad / pgrady);
+    const double grad = dmin(xgrad, ygrad);
+    const double grad2 = grad * grad;
+    q = 2.0 * I.rho * grad2 * limiter * limiter;
+  }
+  return q;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Block-level reduction tails shared by calc_dt and field_summary: every block publishes its
+// partial(s), the last block to arrive (ticket) folds them in a fixed order and writes the result
+// to pinned host memory, then re-arms the ticket.
+template <int N, bool IS_MIN>
+__device__ __forceinline__ void block_reduce_publish(double (&v)[N], double* __restrict__ partials,
+                                                     unsigned int* ticket, double* __restrict__ out,
+                                                     double identity) {
+  __shared__ double sm[N][BX * BY / 32];
+  __shared__ bool last;
+  const int tid = threadIdx.y * BX + threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const unsigned nblocks = gridDim.x * gridDim.y;
+  const unsigned bid = blockIdx.y * gridDim.x + blockIdx.x;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double w = IS_MIN ? warp_min(v[i]) : warp_sum(v[i]);
+    if (lane == 0) sm[i][warp] = w;
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double a = sm[i][0];
+      for (int w = 1; w < BX * BY / 32; ++w) a = IS_MIN ? ((sm[i][w] < a) ? sm[i][w] : a) : a + sm[i][w];
+      partials[(size_t)i * nblocks + bid] = a;
+    }
+    __threadfence();
+    const unsigned t = atomicAdd(ticket, 1u);
+    last = (t == nblocks - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double a = identity;
+    for (unsigned b = tid; b < nblocks; b += BX * BY) {
+      const double p = __ldcg(&partials[(size_t)i * nblocks + b]);
+      a = IS_MIN ? ((p < a) ? p : a) : a + p;
+    }
+    a = IS_MIN ? warp_min(a) : warp_sum(a);
+    if (lane == 0) sm[i][warp] = a;
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double a = sm[i][0];
+      for (int w = 1; w < BX * BY / 32; ++w) a = IS_MIN ? ((sm[i][w] < a) ? sm[i][w] : a) : a + sm[i][w];
+      out[i] = a;
+    }
+    *ticket = 0;
+    __threadfence_system();
+  }
+}
+
+// calc_dt_kernel_c.c:96-144.  8 passes read = 64 B/cell; no per-cell dt_min array is written.
+struct DtParams {
+  double g_small, g_big, dtc_safe, dtu_safe, dtv_safe, dtdiv_safe;
+};
+struct DtIn {
+  double dsx, dsy, vol, ssp, visc, rho, u00, u10, u01, u11, v00, v10, v01, v11, xa0, xa1, ya0, ya1;
+};
+// calc_dt_kernel_c.c:99-133, one cell.  The sqrt and the four divisions are independent chains.
+template <bool SAFE>
+__device__ __forceinline__ double calc_dt_cell(const DtIn& I, const DtParams& P, bool& bad) {
+  typedef Math<SAFE> M;
+  double cc = I.ssp * I.ssp;
+  cc = cc + M::div(2.0 * I.visc, I.rho, bad);
+  cc = dmax(M::sqrt(cc, bad), P.g_small);
+  const double dtct = M::div(P.dtc_safe * dmin(I.dsx, I.dsy), cc, bad);
+  double div = 0.0;
+  double dv1 = (I.u00 + I.u01) * I.xa0;
+  double dv2 = (I.u10 + I.u11) * I.xa1;
+  div = div + dv2 - dv1;
+  const double dtut = M::div(P.dtu_safe * 2.0 * I.vol, dmax(fabs(dv1), dmax(fabs(dv2), P.g_small * I.vol)), bad);
+  dv1 = (I.v00 + I.v10) * I.ya0;
+  dv2 = (I.v01 + I.v11) * I.ya1;
+  div = div + dv2 - dv1;
+  const double dtvt = M::div(P.dtv_safe * 2.0 * I.vol, dmax(fabs(dv1), dmax(fabs(dv2), P.g_small * I.vol)), bad);
+  div = M::div(div, 2.0 * I.vol, bad);
+  // the divergence limit applies to compressing cells only: generic operator in that minority branch
+  const double dtdivt = (div < -P.g_small) ? P.dtdiv_safe * (-1.0 / div) : P.g_big;
+  return dmin(dtct, dmin(dtut, dmin(dtvt, dtdivt)));
+}
+
+}  // namespace clv

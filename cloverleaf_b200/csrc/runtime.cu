@@ -32,6 +32,7 @@ struct Entry {
   Kind kind = CELL;
   int nx = 0, ny = 0;
   size_t doubles = 0;
+  const double* lazy_src = nullptr;  // pending lazy copy: my update range := that of lazy_src's mirror
 };
 
 struct Buffer {
@@ -59,6 +60,10 @@ struct Runtime {
   long long launches = 0;
   long long h2d = 0, d2h = 0;
   bool profiling = false;
+  std::vector<Op> queue;  // deferred calls (resident mode)
+  bool draining = false;
+  bool fuse = true;
+  int lazy_pending = 0;   // number of entries with lazy_src set
   std::map<std::string, Prof> prof;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -147,6 +152,34 @@ Grid grid_of(const int* xmin, const int* xmax, const int* ymin, const int* ymax)
   return grid_of_noflush(xmin, xmax, ymin, ymax);
 }
 
+bool fusion_enabled() { return R.fuse; }
+
+void submit(Op&& op) {
+  if (!R.resident) {
+    op.run();
+    finish();
+    return;
+  }
+  R.queue.push_back(std::move(op));
+  if (R.queue.size() >= 1024) flush_deferred();
+}
+
+void flush_deferred() {
+  if (R.draining || R.queue.empty()) return;
+  R.draining = true;
+  std::vector<Op> q;
+  q.swap(R.queue);
+  for (size_t i = 0; i < q.size();) {
+    size_t used = R.fuse ? fuse_at(q.data(), q.size(), i) : 0;
+    if (used == 0) {
+      q[i].run();
+      used = 1;
+    }
+    i += used;
+  }
+  R.draining = false;
+}
+
 Grid grid_of_noflush(const int* xmin, const int* xmax, const int* ymin, const int* ymax) {
   ensure_init();
   if (*xmin != 1 || *ymin != 1)
@@ -159,6 +192,16 @@ Grid grid_of_noflush(const int* xmin, const int* xmax, const int* ymin, const in
   return g;
 }
 
+static void materialize(Entry& e);
+static void materialize_dependents(const double* host);
+static void materialize_all();
+static void drop_lazy(Entry& e) {
+  if (e.lazy_src) {
+    e.lazy_src = nullptr;
+    R.lazy_pending--;
+  }
+}
+
 static Entry& lookup(const Grid& g, const double* host, Kind kind, bool* fresh) {
   if (!host) fatal("null array pointer passed to a kernel entry point");
   auto it = R.arrays.find(host);
@@ -169,6 +212,8 @@ static Entry& lookup(const Grid& g, const double* host, Kind kind, bool* fresh) 
       return e;
     }
     // same host address re-used with another shape (e.g. a work array): re-create the mirror
+    materialize_dependents(host);
+    drop_lazy(e);
     CLV_CUDA(cudaStreamSynchronize(R.stream));
     CLV_CUDA(cudaFree(e.d));
     if (e.alt) CLV_CUDA(cudaFree(e.alt));
@@ -184,15 +229,65 @@ static Entry& lookup(const Grid& g, const double* host, Kind kind, bool* fresh) 
   return R.arrays.emplace(host, e).first->second;
 }
 
+// ---- lazy copies ----------------------------------------------------------------------------------
+void launch_copy_range(const Grid& g, const double* src, double* dst, Kind kind);  // lagrange.cu
+
+static void materialize(Entry& e) {
+  if (!e.lazy_src) return;
+  auto it = R.arrays.find(e.lazy_src);
+  if (it == R.arrays.end()) fatal("lazy copy source vanished");
+  Grid g{e.nx, e.ny, pitch_for(e.nx)};
+  launch_copy_range(g, it->second.d, e.d, e.kind);
+  e.lazy_src = nullptr;
+  R.lazy_pending--;
+}
+// `host` is about to be modified: perform every pending copy that reads from it
+static void materialize_dependents(const double* host) {
+  if (R.lazy_pending == 0) return;
+  for (auto& kv : R.arrays)
+    if (kv.second.lazy_src == host) materialize(kv.second);
+}
+static void materialize_all() {
+  if (R.lazy_pending == 0) return;
+  for (auto& kv : R.arrays) materialize(kv.second);
+}
+
 double* dev(const Grid& g, const double* host, Kind kind, int access) {
   bool fresh = false;
   Entry& e = lookup(g, host, kind, &fresh);
+  if (R.lazy_pending) {
+    if (e.lazy_src) {
+      if (access == OUT_FULL) {
+        drop_lazy(e);
+      } else {
+        materialize(e);
+      }
+    }
+    if (access & OUT) materialize_dependents(host);
+  }
   // Resident mode: the host copy is authoritative only the first time the address is seen.
   // Copy-in/out mode: it is authoritative on every call (outputs too: a kernel writes only its
   // loop range, the rest of the array must survive the round trip).
   if (fresh || !R.resident) upload(e, host);
-  if (!R.resident && (access & OUT)) R.pending_out.push_back(host);
+  if (!R.resident && (access & (OUT | HALO))) R.pending_out.push_back(host);
   return e.d;
+}
+
+void lazy_copy(const Grid& g, const double* dst_host, const double* src_host, Kind kind) {
+  dev(g, src_host, kind, IN);        // exists, uploaded, itself materialised
+  dev(g, dst_host, kind, OUT_FULL);  // exists; whatever was pending for dst is superseded; dependents of dst done
+  Entry& d = R.arrays.find(dst_host)->second;
+  d.lazy_src = src_host;
+  R.lazy_pending++;
+}
+
+void swap_buffers(const double* host_a, const double* host_b) {
+  auto a = R.arrays.find(host_a), b = R.arrays.find(host_b);
+  if (a == R.arrays.end() || b == R.arrays.end()) fatal("swap_buffers on an unknown array");
+  Entry &x = a->second, &y = b->second;
+  if (x.kind != y.kind || x.nx != y.nx || x.ny != y.ny) fatal("swap_buffers: shape mismatch");
+  if (x.lazy_src || y.lazy_src) fatal("swap_buffers with a lazy copy pending");
+  std::swap(x.d, y.d);
 }
 
 double* dev_alt(const Grid& g, const double* host, Kind kind) {
@@ -307,6 +402,7 @@ void clover_b200_init_(int* device) {
   CLV_CUDA(cudaMemset(R.d_ticket, 0, 16 * sizeof(unsigned int)));
   CLV_CUDA(cudaEventCreate(&R.ev0));
   CLV_CUDA(cudaEventCreate(&R.ev1));
+  if (const char* s = getenv("CLOVER_B200_FUSE")) R.fuse = (atoi(s) != 0);
   R.ready = true;
 }
 
@@ -333,6 +429,7 @@ void clover_b200_finalize_(void) {
 void clover_b200_set_resident_(int* on) {
   ensure_init();
   flush_deferred();
+  materialize_all();
   CLV_CUDA(cudaStreamSynchronize(R.stream));
   R.resident = (*on != 0);
 }
@@ -346,6 +443,7 @@ void clover_b200_invalidate_(void) {
     if (kv.second.alt) CLV_CUDA(cudaFree(kv.second.alt));
   }
   R.arrays.clear();
+  R.lazy_pending = 0;
   for (auto& kv : R.buffers) CLV_CUDA(cudaFree(kv.second.d));
   R.buffers.clear();
   R.pending_out.clear();
@@ -356,6 +454,8 @@ void clover_b200_forget_(double* host) {
   flush_deferred();
   auto it = R.arrays.find(host);
   if (it != R.arrays.end()) {
+    materialize_dependents(host);
+    drop_lazy(it->second);
     CLV_CUDA(cudaStreamSynchronize(R.stream));
     CLV_CUDA(cudaFree(it->second.d));
     if (it->second.alt) CLV_CUDA(cudaFree(it->second.alt));
@@ -374,6 +474,8 @@ void clover_b200_upload_(double* host) {
   flush_deferred();
   auto it = R.arrays.find(host);
   if (it == R.arrays.end()) return;  // never seen: the first use uploads it anyway
+  materialize_dependents(host);
+  drop_lazy(it->second);
   upload(it->second, host);
 }
 
@@ -382,6 +484,7 @@ void clover_b200_download_(double* host) {
   flush_deferred();
   auto it = R.arrays.find(host);
   if (it == R.arrays.end()) fatal("download of an array the library has never seen");
+  materialize(it->second);
   download(it->second, host);
   CLV_CUDA(cudaStreamSynchronize(R.stream));
 }
@@ -393,7 +496,10 @@ void clover_b200_sync_to_host_(int* fields) {
   for (int f = 0; f < 15; ++f) {
     if (fields && fields[f] != 1) continue;
     auto it = R.arrays.find(C.field[f]);
-    if (it != R.arrays.end()) download(it->second, C.field[f]);
+    if (it != R.arrays.end()) {
+      materialize(it->second);
+      download(it->second, C.field[f]);
+    }
   }
   CLV_CUDA(cudaStreamSynchronize(R.stream));
 }
@@ -420,11 +526,21 @@ void clover_b200_register_chunk_(int* xmin, int* xmax, int* ymin, int* ymax, int
   for (int i = 0; i < 15; ++i) C.field[i] = f[i];
 }
 
-void clover_b200_launch_count_(long long* n) { *n = R.launches; }
+void clover_b200_launch_count_(long long* n) {
+  flush_deferred();
+  *n = R.launches;
+}
 
 void clover_b200_profile_(int* on) {
   ensure_init();
+  flush_deferred();
   R.profiling = (*on != 0);
+}
+
+void clover_b200_set_fusion_(int* on) {
+  ensure_init();
+  flush_deferred();
+  R.fuse = (*on != 0);
 }
 
 void clover_b200_profile_reset_(void) { R.prof.clear(); }
@@ -463,6 +579,7 @@ extern "C" {
 // Record event `slot` (0..7) on the library's stream.
 void clover_b200_event_record_(int* slot) {
   clv::ensure_init();
+  clv::flush_deferred();
   if (*slot < 0 || *slot >= 8) clv::fatal("event slot %d", *slot);
   if (!g_events[*slot]) CLV_CUDA(cudaEventCreate(&g_events[*slot]));
   CLV_CUDA(cudaEventRecord(g_events[*slot], clv::stream()));

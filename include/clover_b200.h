@@ -174,6 +174,14 @@ void clover_b200_finalize_(void);
  * outputs before returning (a literal drop-in, used by the per-kernel A/B tests and the
  * host-buffer `e2e` measurement). */
 void clover_b200_set_resident_(int *on);
+/* Deferred execution (resident mode only).  Kernel entry points record their call and return; the
+ * recorded stretch runs -- in order -- as soon as a result has to reach the host (calc_dt's dt,
+ * field_summary's sums, any download / pack / sync below).  With fusion on (default, or
+ * $CLOVER_B200_FUSE=0 to disable) recognised runs of calls execute as one kernel each:
+ * ideal_gas+viscosity+calc_dt, PdV predictor+ideal_gas+revert, accelerate+PdV corrector+flux_calc,
+ * advec_mom x/y velocity pairs, and reset_field / revert become buffer swaps / lazy copies.  Array
+ * contents at every host-observable point are bit-identical with fusion on or off. */
+void clover_b200_set_fusion_(int *on);
 /* Forget all device mirrors (the host arrays were modified behind the library's back). */
 void clover_b200_invalidate_(void);
 /* Forget the mirror of ONE host array (call before the host frees / re-uses that address). */
