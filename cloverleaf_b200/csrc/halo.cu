@@ -95,6 +95,30 @@ __global__ void __launch_bounds__(256)
   F.p[idx2(pitch, jd, kd)] = sign * F.p[idx2(pitch, js, ks)];
 }
 
+// Chunks narrower than depth+1 cells: the mirror source of a depth-2 halo cell can itself be a halo cell that an
+// earlier loop of the same call wrote (or has not written yet), so the one-pass composition above does not hold.
+// Here the reference's four loops run as four launches in the reference's order (bottom, top, left, right).
+__global__ void __launch_bounds__(256)
+    update_halo_seq_kernel(FieldTable T, int nx, int ny, int pitch, int depth, int phase) {
+  const FieldDesc F = T.f[blockIdx.y];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (phase < 2) {
+    const int W = nx + F.x_inc + 2 * depth;
+    if (t >= depth * W) return;
+    const int k = t / W + 1, j = 1 - depth + (t % W);
+    const int kd = phase == 0 ? 1 - k : ny + F.y_inc + k;
+    const int ks = phase == 0 ? F.m + k : ny + F.y_inc + (1 - F.m) - k;
+    F.p[idx2(pitch, j, kd)] = F.sy * F.p[idx2(pitch, j, ks)];
+  } else {
+    const int H = ny + F.y_inc + 2 * depth;
+    if (t >= depth * H) return;
+    const int j = t / H + 1, k = 1 - depth + (t % H);
+    const int jd = phase == 2 ? 1 - j : nx + F.x_inc + j;
+    const int js = phase == 2 ? F.m + j : nx + F.x_inc + (1 - F.m) - j;
+    F.p[idx2(pitch, jd, k)] = F.sx * F.p[idx2(pitch, js, k)];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // pack_kernel_c.c:29-439, all fields of one face in one launch.  face: 0 left, 1 right, 2 bottom, 3 top.
 // Message index (0-based): left/right  off + (jj-1) + (k+depth-1)*depth,  k = 1-depth .. ny+y_inc+depth
@@ -339,6 +363,16 @@ static FieldTable field_table(const Grid& g, const HaloArgs& h, int depth, int e
 void run_update_halo(const Grid& g, const HaloArgs& h) {
   const FieldTable T = field_table(g, h, h.depth, 0);
   if (T.n > 0 && (h.ext[0] || h.ext[1] || h.ext[2] || h.ext[3])) {
+    if (g.nx < h.depth + 1 || g.ny < h.depth + 1) {
+      for (int phase = 0; phase < 4; ++phase) {
+        if (!h.ext[phase < 2 ? 2 + phase : phase - 2]) continue;  // ext = {left, right, bottom, top}
+        const int strip = h.depth * ((phase < 2 ? g.nx : g.ny) + 1 + 2 * h.depth);
+        const dim3 grid((unsigned)((strip + 255) / 256), (unsigned)T.n);
+        LaunchScope ls("update_halo_seq");
+        update_halo_seq_kernel<<<grid, 256, 0, stream()>>>(T, g.nx, g.ny, g.pitch, h.depth, phase);
+      }
+      return;
+    }
     const int ring = 2 * h.depth * (g.nx + 1 + 2 * h.depth) + 2 * h.depth * (g.ny + 1);
     const dim3 grid((unsigned)((ring + 255) / 256), (unsigned)T.n);
     LaunchScope ls("update_halo");

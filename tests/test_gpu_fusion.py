@@ -44,7 +44,8 @@ def fresh(b200):
     b200.clover_b200_invalidate_()
 
 
-@pytest.mark.parametrize("nx,ny,steps", [(64, 48, 7), (64, 48, 8), (250, 130, 21), (33, 2, 5), (2, 40, 6), (130, 97, 30)])
+@pytest.mark.parametrize("nx,ny,steps", [(64, 48, 7), (64, 48, 8), (250, 130, 21), (33, 2, 5), (2, 40, 6), (1, 1, 3), (3, 1, 3),
+                                         (130, 97, 30)])
 def test_fused_equals_unfused_equals_oracle(fresh, nx, ny, steps):
     deck = _deck(nx, ny)
     o = Driver(deck, ORACLE_PORT, end_step=steps); o.run()

@@ -59,7 +59,8 @@ def test_kernel_matches_oracle(cuda, oracle_lib, case, nx, ny):
 
 
 @pytest.mark.parametrize("case", kc.halo_cases(), ids=lambda c: c[0])
-@pytest.mark.parametrize("nx,ny", [(11, 7), (40, 3)])
+# chunks narrower than depth+1 take the four-launch sequential path (mirror sources inside the halo)
+@pytest.mark.parametrize("nx,ny", [(11, 7), (40, 3), (2, 5), (9, 1), (1, 1)])
 def test_update_halo_matches_oracle(cuda, oracle_lib, case, nx, ny):
     _, depth, nb = case
     S0 = kc.make_state(nx, ny, seed=3)
