@@ -24,10 +24,13 @@
 #include "clover_b200.h"
 #include "common.cuh"
 #include "lagrange.cuh"
+#include "tma.cuh"
 
 namespace clv {
 
 // from runtime.cu
+bool tma_enabled();
+int sm_count();
 bool chunk_registered();
 const int* chunk_neighbours();
 
@@ -253,6 +256,186 @@ __global__ void __launch_bounds__(CT_W* CT_BY)
       A.density1[c] = rho0 * vc;
     }
   }
+}
+
+// ---- C with TMA tile staging (tma.cuh) ------------------------------------------------------------------------
+// Persistent CTAs; a tile is LT_W x LT_H slots.  The nine input fields arrive as (LT_W+4) x (LT_H+2) boxes with
+// corner (j0-2, k0-1): cells j0-1..j0+LT_W feed the nodal masses of vertices j0..j0+LT_W, and the same box holds
+// the vertices / faces of the tile plus the extra row and column.  The arithmetic is that of
+// lagrange_correct_kernel, statement for statement.
+constexpr int LT_H = 8, LT_BH = LT_H + 2, LT_NARR = 9;
+constexpr int LT_OX = 2;  // box corner at j0-2: TMA needs a 16-byte aligned start, i.e. an even dim-0 coordinate (tma.cuh)
+enum { LA_XAREA = 0, LA_YAREA, LA_VOLUME, LA_DENSITY0, LA_ENERGY0, LA_PRESSURE, LA_VISCOSITY, LA_XVEL0, LA_YVEL0 };
+struct CorrectMaps {
+  CUtensorMap m[LT_NARR];
+};
+struct CorrectOut {
+  double *xvel1, *yvel1, *density1, *energy1, *vol_flux_x, *vol_flux_y;
+};
+
+// RPT = slot rows per thread (independent dependency chains per thread), STAGES = ring depth, CPS = CTAs per SM.
+// W = tile width in slots (even), box = (W+4) x (LT_H+2).
+template <int W, int RPT, int STAGES, int CPS>
+struct CorrectCfg {
+  static constexpr int NT = W * LT_H / RPT;
+  static constexpr int BW = W + 4, VW = W + 1;
+  using Ring = TileRing<LT_NARR, BW, LT_BH, STAGES>;
+  static constexpr int NVERT = VW * (LT_H + 1);
+  static constexpr int VPT = (NVERT + NT - 1) / NT;  // vertices per thread
+  static constexpr int SMEM = Ring::BYTES + 2 * NVERT * 8 + 128;
+};
+
+template <int W, int RPT, int STAGES, int CPS>
+__global__ void __launch_bounds__(W* LT_H / RPT, CPS)
+    lagrange_correct_tma_kernel(const __grid_constant__ CorrectMaps M, CorrectOut O, int nx, int ny, int pitch,
+                                double dt, int ntx, int ntiles) {
+  using Cfg = CorrectCfg<W, RPT, STAGES, CPS>;
+  constexpr int NT = Cfg::NT, VPT = Cfg::VPT, NVERT = Cfg::NVERT, ROWS = LT_H / RPT, LT_W = W, LT_BW = Cfg::BW, LT_VW = Cfg::VW;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = align128(smem_raw);
+  typename Cfg::Ring ring;
+  ring.init(smem);
+  double* __restrict__ su1 = reinterpret_cast<double*>(smem + Cfg::Ring::BYTES);
+  double* __restrict__ sv1 = su1 + NVERT;
+  const int tid = threadIdx.x, lx = tid % LT_W, ty = tid / LT_W;
+  const int G = gridDim.x;
+  const int jmax = nx + 1, kmax = ny + 1;
+  // box corner of tile t in tensor coordinates: element (j,k) is at (j + XOFF, k + 1)
+  auto issue_tile = [&](int stage, int t) {
+    const int j0 = 1 + (t % ntx) * LT_W, k0 = 1 + (t / ntx) * LT_H;
+    ring.issue(M.m, stage, j0 - LT_OX + XOFF, k0 - 1 + 1);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+      const int t = (int)blockIdx.x + s * G;
+      if (t < ntiles) issue_tile(s, t);
+    }
+  }
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += G, ++it) {
+    const int stage = it % STAGES;
+    if (tid == 0) {
+      const int tn = t + (STAGES - 1) * G;  // its stage was released by the barrier that ended iteration it-1
+      if (tn < ntiles) issue_tile((stage + STAGES - 1) % STAGES, tn);
+    }
+    const int j0 = 1 + (t % ntx) * LT_W, k0 = 1 + (t / ntx) * LT_H;
+    ring.wait(stage, (uint32_t)((it / STAGES) & 1));
+    const double* __restrict__ sxa = ring.tile(stage, LA_XAREA);
+    const double* __restrict__ sya = ring.tile(stage, LA_YAREA);
+    const double* __restrict__ svol = ring.tile(stage, LA_VOLUME);
+    const double* __restrict__ sd0 = ring.tile(stage, LA_DENSITY0);
+    const double* __restrict__ se0 = ring.tile(stage, LA_ENERGY0);
+    const double* __restrict__ sp = ring.tile(stage, LA_PRESSURE);
+    const double* __restrict__ sq = ring.tile(stage, LA_VISCOSITY);
+    const double* __restrict__ su0 = ring.tile(stage, LA_XVEL0);
+    const double* __restrict__ sv0 = ring.tile(stage, LA_YVEL0);
+    // ---- phase 1: new velocities of the (LT_W+1) x (LT_H+1) vertices (accelerate_kernel_c.c:56-95) -------------
+    {
+      double xv[VPT], yv[VPT];
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        const int v = tid + i * NT;
+        const int vc = v < NVERT ? v : NVERT - 1;
+        const int vx = vc % LT_VW, vy = vc / LT_VW;
+        const int c11 = (vy + 1) * LT_BW + vx + LT_OX, c01 = c11 - 1, c10 = c11 - LT_BW, c00 = c10 - 1;
+        const double d00 = sd0[c00], d10 = sd0[c10], d11 = sd0[c11], d01 = sd0[c01];
+        const double w00 = svol[c00], w10 = svol[c10], w11 = svol[c11], w01 = svol[c01];
+        const double xa1 = sxa[c11], xa0 = sxa[c10];
+        const double ya1 = sya[c11], ya0 = sya[c01];
+        const double p11 = sp[c11], p01 = sp[c01], p10 = sp[c10], p00 = sp[c00];
+        const double q11 = sq[c11], q01 = sq[c01], q10 = sq[c10], q00 = sq[c00];
+        const double xv0 = su0[c11], yv0 = sv0[c11];
+        const double nodal_mass = (d00 * w00 + d10 * w10 + d11 * w11 + d01 * w01) * 0.25;
+        const double s = 0.5 * dt / nodal_mass;
+        double x = xv0 - s * (xa1 * (p11 - p01) + xa0 * (p10 - p00));
+        double y = yv0 - s * (ya1 * (p11 - p10) + ya0 * (p01 - p00));
+        xv[i] = x - s * (xa1 * (q11 - q01) + xa0 * (q10 - q00));
+        yv[i] = y - s * (ya1 * (q11 - q10) + ya0 * (q01 - q00));
+      }
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        const int v = tid + i * NT;
+        if (v < NVERT) {
+          su1[v] = xv[i];
+          sv1[v] = yv[i];
+          const int vx = v % LT_VW, vy = v / LT_VW;
+          const int j = j0 + vx, k = k0 + vy;
+          if (vx < LT_W && vy < LT_H && j <= jmax && k <= kmax) {
+            const size_t c = idx2(pitch, j, k);
+            O.xvel1[c] = xv[i];
+            O.yvel1[c] = yv[i];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: faces (flux_calc_kernel_c.c:55-58, :67-70) and cells (PdV_kernel_c.c:117-163) ------------------
+    {
+      double fx[RPT], fy[RPT], e1[RPT], d1[RPT];
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        const int ly = ty + r * ROWS;
+        const int b = (ly + 1) * LT_BW + lx + LT_OX;  // slot (j,k) inside the box
+        const int v = ly * LT_VW + lx;                // vertex (j,k) inside su1/sv1
+        const double x00 = su0[b], x10 = su0[b + 1], x01 = su0[b + LT_BW], x11 = su0[b + LT_BW + 1];
+        const double y00 = sv0[b], y10 = sv0[b + 1], y01 = sv0[b + LT_BW], y11 = sv0[b + LT_BW + 1];
+        const double a00 = su1[v], a10 = su1[v + 1], a01 = su1[v + LT_VW], a11 = su1[v + LT_VW + 1];
+        const double b00 = sv1[v], b10 = sv1[v + 1], b01 = sv1[v + LT_VW], b11 = sv1[v + LT_VW + 1];
+        const double xa0 = sxa[b], ya0 = sya[b];
+        const double xa1 = sxa[b + 1], ya1 = sya[b + LT_BW];
+        const double vol = svol[b], rho0 = sd0[b], pres = sp[b], visc = sq[b], en0 = se0[b];
+        fx[r] = 0.25 * dt * xa0 * (x00 + x01 + a00 + a01);
+        fy[r] = 0.25 * dt * ya0 * (y00 + y10 + b00 + b10);
+        const double left = xa0 * (x00 + x01 + a00 + a01) * 0.25 * dt;
+        const double right = xa1 * (x10 + x11 + a10 + a11) * 0.25 * dt;
+        const double bottom = ya0 * (y00 + y10 + b00 + b10) * 0.25 * dt;
+        const double top = ya1 * (y01 + y11 + b01 + b11) * 0.25 * dt;
+        const double total = right - left + top - bottom;
+        const double vc = vol / (vol + total);
+        const double recip = 1.0 / vol;
+        const double de = (pres / rho0 + ddiv(visc, rho0)) * total * recip;
+        e1[r] = en0 - de;
+        d1[r] = rho0 * vc;
+      }
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        const int j = j0 + lx, k = k0 + ty + r * ROWS;
+        if (j <= jmax && k <= kmax) {
+          const size_t c = idx2(pitch, j, k);
+          if (k <= ny) O.vol_flux_x[c] = fx[r];
+          if (j <= nx) O.vol_flux_y[c] = fy[r];
+          if (j <= nx && k <= ny) {
+            O.energy1[c] = e1[r];
+            O.density1[c] = d1[r];
+          }
+        }
+      }
+    }
+    __syncthreads();  // stage and su1/sv1 are free again
+  }
+}
+
+template <int W, int RPT, int STAGES, int CPS>
+static void launch_correct_tma(const CorrectArgs& A, const Grid& g, double dt) {
+  using Cfg = CorrectCfg<W, RPT, STAGES, CPS>;
+  constexpr int LT_W = W;
+  CorrectMaps M;
+  const double* in[LT_NARR] = {A.xarea, A.yarea, A.volume, A.density0, A.energy0, A.pressure, A.viscosity, A.xvel0, A.yvel0};
+  for (int a = 0; a < LT_NARR; ++a) M.m[a] = *tensor_map_for(g, in[a], Cfg::BW, LT_BH);
+  const CorrectOut O{A.xvel1, A.yvel1, A.density1, A.energy1, A.vol_flux_x, A.vol_flux_y};
+  static bool configured = false;
+  if (!configured) {
+    CLV_CUDA(cudaFuncSetAttribute(lagrange_correct_tma_kernel<W, RPT, STAGES, CPS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    configured = true;
+  }
+  const int ntx = (g.nx + 1 + LT_W - 1) / LT_W, nty = (g.ny + 1 + LT_H - 1) / LT_H;
+  const int ntiles = ntx * nty;
+  const int cap = sm_count() * CPS;
+  const int ctas = ntiles < cap ? ntiles : cap;
+  lagrange_correct_tma_kernel<W, RPT, STAGES, CPS><<<ctas, Cfg::NT, Cfg::SMEM, stream()>>>(M, O, g.nx, g.ny, g.pitch, dt, ntx,
+                                                                                       ntiles);
 }
 
 // single-call host launchers (lagrange.cu, advec.cu)
@@ -484,6 +667,21 @@ static size_t fuse_correct(const Op* q, size_t n, size_t i) {
   A.energy1 = dev(g, energy1, CELL, OUT_FULL);
   A.vol_flux_x = dev(g, vol_flux_x, XFACE, OUT);
   A.vol_flux_y = dev(g, vol_flux_y, YFACE, OUT);
+  if (tma_enabled()) {
+    static int cfg = -1;
+    if (cfg < 0) cfg = getenv("CLOVER_B200_LT_CFG") ? atoi(getenv("CLOVER_B200_LT_CFG")) : 1;
+    LaunchScope ls("lagrange_correct_tma");
+    switch (cfg) {
+      case 0: launch_correct_tma<32, 2, 2, 3>(A, g, ac.sv[0]); break;
+      case 2: launch_correct_tma<32, 2, 2, 4>(A, g, ac.sv[0]); break;
+      case 3: launch_correct_tma<32, 1, 2, 3>(A, g, ac.sv[0]); break;
+      case 4: launch_correct_tma<32, 2, 3, 2>(A, g, ac.sv[0]); break;
+      case 5: launch_correct_tma<64, 2, 2, 2>(A, g, ac.sv[0]); break;
+      case 6: launch_correct_tma<32, 4, 2, 4>(A, g, ac.sv[0]); break;
+      default: launch_correct_tma<64, 2, 2, 2>(A, g, ac.sv[0]); break;
+    }
+    return 3;
+  }
   const dim3 grid((unsigned)((g.nx + 1 + CT_W - 1) / CT_W), (unsigned)((g.ny + 1 + CT_H - 1) / CT_H));
   LaunchScope ls("lagrange_correct_fused");
   lagrange_correct_kernel<<<grid, dim3(CT_W, CT_BY), 0, stream()>>>(A, g.nx, g.ny, g.pitch, ac.sv[0]);

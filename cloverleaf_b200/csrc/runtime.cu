@@ -5,12 +5,14 @@
 #include <cstdarg>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <string>
 #include <unordered_map>
 #include <vector>
 
 #include "clover_b200.h"
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace clv {
 
@@ -63,12 +65,16 @@ struct Runtime {
   std::vector<Op> queue;  // deferred calls (resident mode)
   bool draining = false;
   bool fuse = true;
+  bool tma = true;
+  int sms = 148;
   int lazy_pending = 0;   // number of entries with lazy_src set
   std::map<std::string, Prof> prof;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 Runtime R;
+
+void drop_tensor_maps();  // defined with the tensor-map cache below
 
 bool is_2d(Kind k) { return k <= YFACE; }
 int host_row(Kind k, int nx) { return (k == CELL || k == YFACE) ? nx + 4 : nx + 5; }
@@ -153,6 +159,8 @@ Grid grid_of(const int* xmin, const int* xmax, const int* ymin, const int* ymax)
 }
 
 bool fusion_enabled() { return R.fuse; }
+bool tma_enabled() { return R.tma; }
+int sm_count() { return R.sms; }
 
 void submit(Op&& op) {
   if (!R.resident) {
@@ -218,6 +226,7 @@ static Entry& lookup(const Grid& g, const double* host, Kind kind, bool* fresh) 
     CLV_CUDA(cudaFree(e.d));
     if (e.alt) CLV_CUDA(cudaFree(e.alt));
     R.arrays.erase(it);
+    drop_tensor_maps();
   }
   Entry e;
   e.kind = kind;
@@ -368,6 +377,55 @@ double* partials(size_t doubles) {
   return R.d_partials;
 }
 
+// ---- TMA tensor maps (tma.cuh) ------------------------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver-API entry point; it is fetched through the runtime so that the library
+// does not link libcuda.  A map depends only on (address, pitch, rows, box), so entries stay valid for as long
+// as an allocation of that shape lives at that address; the cache is dropped whenever mirrors are freed.
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+struct MapKey {
+  const void* p;
+  int pitch, rows, bw, bh;
+  bool operator<(const MapKey& o) const {
+    return std::tie(p, pitch, rows, bw, bh) < std::tie(o.p, o.pitch, o.rows, o.bw, o.bh);
+  }
+};
+std::map<MapKey, CUtensorMap*> g_maps;
+void drop_tensor_maps() {
+  for (auto& kv : g_maps) free(kv.second);
+  g_maps.clear();
+}
+}  // namespace
+
+const CUtensorMap* tensor_map_for(const Grid& g, const double* dev_ptr, int box_w, int box_h) {
+  const MapKey key{dev_ptr, g.pitch, g.ny + 6, box_w, box_h};
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) return it->second;
+  if (!g_encode_tiled) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CLV_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) fatal("cuTensorMapEncodeTiled is not available in this driver");
+    g_encode_tiled = (EncodeTiledFn)fn;
+  }
+  CUtensorMap* m = nullptr;
+  if (posix_memalign((void**)&m, 64, sizeof(CUtensorMap)) != 0) fatal("out of host memory");
+  const cuuint64_t dims[2] = {(cuuint64_t)g.pitch, (cuuint64_t)(g.ny + 6)};
+  const cuuint64_t strides[1] = {(cuuint64_t)g.pitch * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)dev_ptr, dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    fatal("cuTensorMapEncodeTiled failed (%d) for pitch %d rows %d box %dx%d", (int)r, g.pitch, g.ny + 6, box_w, box_h);
+  g_maps[key] = m;
+  return m;
+}
+
 // used by halo.cu
 bool chunk_registered() { return C.set; }
 int chunk_nx() { return C.nx; }
@@ -403,6 +461,8 @@ void clover_b200_init_(int* device) {
   CLV_CUDA(cudaEventCreate(&R.ev0));
   CLV_CUDA(cudaEventCreate(&R.ev1));
   if (const char* s = getenv("CLOVER_B200_FUSE")) R.fuse = (atoi(s) != 0);
+  if (const char* s = getenv("CLOVER_B200_TMA")) R.tma = (atoi(s) != 0);  // A/B switch for profiling
+  R.sms = p.multiProcessorCount;
   R.ready = true;
 }
 
@@ -443,6 +503,7 @@ void clover_b200_invalidate_(void) {
     if (kv.second.alt) CLV_CUDA(cudaFree(kv.second.alt));
   }
   R.arrays.clear();
+  drop_tensor_maps();
   R.lazy_pending = 0;
   for (auto& kv : R.buffers) CLV_CUDA(cudaFree(kv.second.d));
   R.buffers.clear();
@@ -460,6 +521,7 @@ void clover_b200_forget_(double* host) {
     CLV_CUDA(cudaFree(it->second.d));
     if (it->second.alt) CLV_CUDA(cudaFree(it->second.alt));
     R.arrays.erase(it);
+    drop_tensor_maps();
   }
   auto ib = R.buffers.find(host);
   if (ib != R.buffers.end()) {

@@ -1,0 +1,115 @@
+// tma.cuh -- TMA tile staging for the streaming stencil kernels (sm_100a).
+//
+// Why: the fp64 kernels hold 50-130 registers per thread, so only 16-32 warps per SM are resident and the bytes
+// they keep in flight with ordinary loads (~30 KB/SM) cannot cover HBM latency (profiles/r01b, r01e: DRAM 35-60 %,
+// dominant stall long_scoreboard).  Here a persistent CTA walks over tiles of the chunk; ONE thread asks the TMA
+// unit (cp.async.bulk.tensor.2d, SASS UTMALDG) to copy the stencil neighbourhood of a LATER tile -- a
+// (TW+halo) x (TH+halo) box of every input field -- into a ring of shared-memory stages while all threads compute
+// the current tile out of shared memory.  Bytes in flight are bounded by shared memory (up to ~150 KB/SM), cost no
+// registers and no issue slots, and the address arithmetic / clamping of the halo loads disappears: boxes that
+// stick out of the allocation are zero-filled by the hardware.
+//
+// Every field uses the same pitched layout (common.cuh), so one tensor-map shape serves all of them:
+//     dim0 = pitch doubles (unit stride), dim1 = ny+6 rows, row stride = pitch*8 B (a multiple of 128 B);
+//     element (j,k) sits at coordinates (j + XOFF, k + 1).
+// Measured on B200: the first byte of a box must be 16-byte aligned (an odd dim-0 coordinate of an fp64 tensor
+// raises cudaErrorIllegalInstruction), so boxes start at an ODD j (XOFF is odd): tiles start at j0 = 1 + n*TW
+// with TW even, and a box that needs column j0-1 starts at j0-2.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace clv {
+
+// Host: tensor map of `dev_ptr` (a field in the pitched layout of grid g) with a box_w x box_h box; cached.
+const CUtensorMap* tensor_map_for(const Grid& g, const double* dev_ptr, int box_w, int box_h);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// generic-proxy accesses to shared memory (the reads of the tile that used this stage before) are ordered before
+// the async-proxy writes of the TMA load issued next
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// 2-D tile load: box of `map` with its (dim0, dim1) corner at (x, y) -> dst; completion (bytes) on `bar`
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)map) : "memory");
+}
+
+// Ring of STAGES shared-memory stages, each holding NARR boxes of BW x BH doubles (each box padded to 128 B).
+template <int NARR, int BW, int BH, int STAGES>
+struct TileRing {
+  static constexpr int BOX_BYTES = BW * BH * 8;
+  static constexpr int ARR_BYTES = (BOX_BYTES + 127) / 128 * 128;
+  static constexpr int STAGE_BYTES = NARR * ARR_BYTES;
+  static constexpr int BYTES = STAGES * STAGE_BYTES + STAGES * 8;  // + the full barriers
+  static_assert((BW * 8) % 16 == 0, "TMA: inner box extent must be a multiple of 16 bytes");
+  static_assert(BW <= 256 && BH <= 256, "TMA: box extents are at most 256");
+  unsigned char* base;  // 128-byte aligned
+  uint64_t* full;
+
+  __device__ __forceinline__ void init(unsigned char* smem_aligned) {
+    base = smem_aligned;
+    full = reinterpret_cast<uint64_t*>(smem_aligned + STAGES * STAGE_BYTES);
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+      mbar_init_fence();
+    }
+    __syncthreads();
+  }
+  __device__ __forceinline__ const double* tile(int stage, int a) const {
+    return reinterpret_cast<const double*>(base + stage * STAGE_BYTES + a * ARR_BYTES);
+  }
+  // one thread: load the boxes with corner (x, y) of all NARR maps into `stage`
+  // (x must be even, see the header comment)
+  __device__ __forceinline__ void issue(const CUtensorMap* maps, int stage, int x, int y) {
+    fence_proxy_async_smem();
+    mbar_arrive_expect_tx(&full[stage], (uint32_t)(NARR * BOX_BYTES));
+#pragma unroll
+    for (int a = 0; a < NARR; ++a)
+      tma_load_2d(base + stage * STAGE_BYTES + a * ARR_BYTES, &maps[a], x, y, &full[stage]);
+  }
+  __device__ __forceinline__ void wait(int stage, uint32_t parity) { mbar_wait(&full[stage], parity); }
+};
+
+__device__ __forceinline__ unsigned char* align128(unsigned char* p) {
+  return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 127) & ~(uintptr_t)127);
+}
+#endif
+
+}  // namespace clv
