@@ -1,0 +1,295 @@
+// advec_tma.cu -- the advective remap with TMA tile staging (tma.cuh): persistent CTAs, the stencil neighbourhood of
+// a tile arrives in shared memory as one box per field, the per-node / per-face intermediates (node fluxes, node
+// masses, limited fluxes) are exchanged between the threads of a CTA through shared memory, and nothing but the
+// final fields goes back to HBM.  Same arithmetic, statement for statement, as advec.cu (which remains the
+// single-call path: copy-in/out mode, fusion off).
+//
+// advec_mom, both velocity components in one launch (advec_mom_kernel_c.c:69-286).  `s` is the sweep axis:
+//   A  node_flux(s)      s = s0-2 .. s0+NS      (:124-134 / :205-214)   NS = nodes of the tile along the sweep
+//      node_mass_post(s) s = s0-1 .. s0+NS      (:135-150 / :216-231)
+//   B  mom_flux(s)       s = s0-1 .. s0+NS-1    (:159-189 / :240-270)   node_mass_pre = post - flux(s-1) + flux(s)
+//   C  vel1(s)           s = s0   .. s0+NS-1    (:191-201 / :272-282)
+// Thread grid TX x TY, RPT rows per thread.  x sweeps: the tile is (TX-4) x (TY*RPT) nodes, so that the TX threads
+// of a row cover the TX-1 node fluxes, TX-3 momentum fluxes and TX-4 nodes of that row in one round each
+// (plane positions 0..TX-2, 1..TX-3 and 2..TX-3).
+// y sweeps: the tile is TX x (TY*RPT-4) nodes for the same reason along k.
+#include "clover_b200.h"
+#include "advec.cuh"
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace clv {
+
+bool tma_enabled();
+int sm_count();
+
+// the halo ring (everything outside the update range 1..nx+e x 1..ny+e of the Fortran extent) is carried over to
+// the new buffer by all CTAs together
+__device__ __forceinline__ void ring_copy(const double* __restrict__ src, double* __restrict__ dst, int nx, int ny,
+                                          int pitch, int e, int t0, int nt) {
+  const int W = nx + 4 + e, H = ny + 4 + e;
+  const int n_bt = 4 * W, n_lr = 4 * (H - 4);
+  for (int t = t0; t < n_bt + n_lr; t += nt) {
+    int j, k;
+    if (t < n_bt) {
+      const int r = t / W;
+      j = -1 + t % W;
+      k = r < 2 ? -1 + r : ny + e + (r - 1);
+    } else {
+      const int u = t - n_bt, c = u / (H - 4);
+      k = 1 + u % (H - 4);
+      j = c < 2 ? -1 + c : nx + e + (c - 1);
+    }
+    const size_t i = idx2(pitch, j, k);
+    dst[i] = src[i];
+  }
+}
+
+enum { MA_VOLUME = 0, MA_DENSITY1, MA_MASS_FLUX, MA_VEL_A, MA_VEL_B, MA_VOL_FLUX, MA_NARR };
+
+template <int DIR, int TX, int TY, int RPT, int STAGES, int CPS>
+struct MomCfg {
+  static constexpr int NT = TX * TY;
+  static constexpr int ROWS = TY * RPT;
+  static constexpr int W = DIR == 1 ? TX - 4 : TX;          // nodes per tile along x
+  static constexpr int H = DIR == 1 ? ROWS : ROWS - 4;      // nodes per tile along y
+  static constexpr int BW = DIR == 1 ? TX : TX + 4;         // box: x from j0-2
+  static constexpr int BH = DIR == 1 ? H + 2 : H + 4;       // box: y from k0-1 (x sweep) / k0-2 (y sweep)
+  static constexpr int OX = 2, OY = DIR == 1 ? 1 : 2;
+  using Ring = TileRing<MA_NARR, BW, BH, STAGES>;
+  static constexpr int NI = TX * ROWS;                      // one intermediate plane: thread-grid shaped
+  static constexpr int SMEM = Ring::BYTES + 4 * NI * 8 + 128;
+};
+struct MomMaps {
+  CUtensorMap m[MA_NARR];
+};
+
+// MS = mom_sweep = direction + 2*(sweep-1)
+template <int DIR, int MS, int TX, int TY, int RPT, int STAGES, int CPS>
+__global__ void __launch_bounds__(TX* TY, CPS)
+    advec_mom_tma_kernel(const __grid_constant__ MomMaps M, const double* __restrict__ va_old, double* __restrict__ va_new,
+                         const double* __restrict__ vb_old, double* __restrict__ vb_new,
+                         const double* __restrict__ celld, int nx, int ny, int pitch, int ntx, int ntiles) {
+  using Cfg = MomCfg<DIR, TX, TY, RPT, STAGES, CPS>;
+  constexpr int NT = Cfg::NT, W = Cfg::W, H = Cfg::H, BW = Cfg::BW, NI = Cfg::NI, OX = Cfg::OX, OY = Cfg::OY;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = align128(smem_raw);
+  typename Cfg::Ring ring;
+  ring.init(smem);
+  double* __restrict__ s_nf = reinterpret_cast<double*>(smem + Cfg::Ring::BYTES);  // node_flux
+  double* __restrict__ s_np = s_nf + NI;                                           // node_mass_post
+  double* __restrict__ s_ma = s_np + NI;                                           // mom_flux, component a
+  double* __restrict__ s_mb = s_ma + NI;                                           // mom_flux, component b
+  const int tid = threadIdx.x, lx = tid % TX, ty = tid / TX;
+  const int G = gridDim.x;
+  ring_copy(va_old, va_new, nx, ny, pitch, 1, (int)blockIdx.x * NT + tid, G * NT);
+  ring_copy(vb_old, vb_new, nx, ny, pitch, 1, (int)blockIdx.x * NT + tid, G * NT);
+  auto issue_tile = [&](int stage, int t) {
+    const int j0 = 1 + (t % ntx) * W, k0 = 1 + (t / ntx) * H;
+    ring.issue(M.m, stage, j0 - OX + XOFF, k0 - OY + 1);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+      const int t = (int)blockIdx.x + s * G;
+      if (t < ntiles) issue_tile(s, t);
+    }
+  }
+  // the sweep axis in box / plane coordinates: moving one node along the sweep
+  constexpr int SB = DIR == 1 ? 1 : BW;   // box stride along the sweep
+  constexpr int SP = DIR == 1 ? 1 : TX;   // plane stride along the sweep
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += G, ++it) {
+    const int stage = it % STAGES;
+    if (tid == 0) {
+      const int tn = t + (STAGES - 1) * G;
+      if (tn < ntiles) issue_tile((stage + STAGES - 1) % STAGES, tn);
+    }
+    const int j0 = 1 + (t % ntx) * W, k0 = 1 + (t / ntx) * H;
+    // celldx / celldy at the sweep positions s-1, s, s+1 of my nodes (1-D, lower bound -1 -> index s+1; clamped for
+    // the nodes beyond the chunk, whose results are never stored); issued before the wait so that they overlap it
+    double cw[RPT], cwm[RPT], cwp[RPT];
+    {
+      const int smax = (DIR == 1 ? nx : ny) + 2;
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        const int s_node = DIR == 1 ? j0 - 2 + lx : k0 - 2 + ty * RPT + r;
+        cw[r] = celld[clampi(s_node, -1, smax) + 1];
+        cwm[r] = celld[clampi(s_node - 1, -1, smax) + 1];
+        cwp[r] = celld[clampi(s_node + 1, -1, smax) + 1];
+      }
+    }
+    ring.wait(stage, (uint32_t)((it / STAGES) & 1));
+    const double* __restrict__ svol = ring.tile(stage, MA_VOLUME);
+    const double* __restrict__ sd1 = ring.tile(stage, MA_DENSITY1);
+    const double* __restrict__ smf = ring.tile(stage, MA_MASS_FLUX);
+    const double* __restrict__ sva = ring.tile(stage, MA_VEL_A);
+    const double* __restrict__ svb = ring.tile(stage, MA_VEL_B);
+    const double* __restrict__ svf = ring.tile(stage, MA_VOL_FLUX);
+    // Thread (lx, ty) owns the RPT adjacent plane rows ty*RPT + r, plane position p = row*TX + lx.
+    // x sweep: plane column lx <-> node j0-2+lx, plane row <-> node k0+row.
+    // y sweep: plane column lx <-> node j0+lx,   plane row <-> node k0-2+row.
+    // Box position of node (j,k): b = (k-k0+OY)*BW + (j-j0+OX).
+    const int row0 = ty * RPT;
+    const int b0 = DIR == 1 ? (row0 + OY) * BW + lx : row0 * BW + lx + OX;
+    const int p0 = row0 * TX + lx;
+    constexpr int NPS = DIR == 1 ? TX : Cfg::ROWS;  // plane positions along the sweep
+    // ---- A: node_flux (valid at sweep positions 0..NPS-2) and node_mass_post (1..NPS-1) ------------------------------
+    double nf[RPT], np[RPT];
+    {
+      // cell rows k-1 .. k+RPT-1 of the columns j-1 (L) and j (R); post_vol*density1 (:69-121)
+      auto pm = [&](int c) {
+        double post_vol;
+        if (MS == 1) post_vol = svol[c] + svf[c + BW] - svf[c];
+        else if (MS == 2) post_vol = svol[c] + svf[c + 1] - svf[c];
+        else post_vol = svol[c];
+        return sd1[c] * post_vol;
+      };
+      double pmL[RPT + 1], pmR[RPT + 1], m0[RPT + 1], m1[RPT + 1];
+      // x sweep: plane column 0 (node j0-2) would need cell column j0-3, y sweep: plane row 0 (node k0-2) cell row
+      // k0-3; neither node mass is ever used, the index is kept inside the box
+      const int bc = b0 + ((DIR == 1 && lx == 0) ? 1 : 0);
+#pragma unroll
+      for (int i = 0; i <= RPT; ++i) {
+        const int ro = (DIR == 2 && i == 0 && row0 == 0) ? 0 : (i - 1) * BW;
+        pmR[i] = pm(bc + ro);
+        pmL[i] = pm(bc + ro - 1);
+        if (DIR == 1) {  // mass_flux_x(j, k-1+i), (j+1, k-1+i)
+          m0[i] = smf[b0 + (i - 1) * BW];
+          m1[i] = smf[b0 + (i - 1) * BW + 1];
+        } else {         // mass_flux_y(j-1, k+i), (j, k+i)
+          m0[i] = smf[b0 + i * BW - 1];
+          m1[i] = smf[b0 + i * BW];
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        if (DIR == 1) nf[r] = 0.25 * (m0[r] + m0[r + 1] + m1[r] + m1[r + 1]);  // (j,k-1)+(j,k)+(j+1,k-1)+(j+1,k)
+        else          nf[r] = 0.25 * (m0[r] + m1[r] + m0[r + 1] + m1[r + 1]);  // (j-1,k)+(j,k)+(j-1,k+1)+(j,k+1)
+        np[r] = 0.25 * (pmR[r] + pmR[r + 1] + pmL[r] + pmL[r + 1]);            // (j,k-1)+(j,k)+(j-1,k-1)+(j-1,k)
+        s_nf[p0 + r * TX] = nf[r];
+        s_np[p0 + r * TX] = np[r];
+      }
+    }
+    __syncthreads();
+    // ---- B: mom_flux at sweep positions 1 .. NPS-3 ---------------------------------------------------------------------
+    double ma[RPT], mb[RPT], va0[RPT], vb0[RPT], nm_pre[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int ps = DIR == 1 ? lx : row0 + r;
+      const int p = p0 + r * TX, b = b0 + r * BW;
+      const bool mine = ps >= 1 && ps <= NPS - 3;
+      // out-of-range positions read inside the planes / the box and are never stored
+      const int pm1 = ps >= 1 ? p - SP : p, pp1 = ps <= NPS - 2 ? p + SP : p;
+      const int bm1 = ps >= 1 ? b - SB : b, bp1 = ps <= NPS - 2 ? b + SB : b, bp2 = ps <= NPS - 3 ? b + 2 * SB : b;
+      const double f = nf[r], f_m = s_nf[pm1], f_p = s_nf[pp1];
+      nm_pre[r] = np[r] - f_m + f;
+      const double nm_pre_p = s_np[pp1] - f + f_p;
+      const bool neg = f < 0.0;
+      const double width = cw[r], width_dif = neg ? cwp[r] : cwm[r];
+      const double nmp_don = neg ? nm_pre_p : nm_pre[r];
+      const double a_m = sva[bm1], a_0 = sva[b], a_p = sva[bp1], a_pp = sva[bp2];
+      const double b_m = svb[bm1], b_0 = svb[b], b_p = svb[bp1], b_pp = svb[bp2];
+      va0[r] = a_0;
+      vb0[r] = b_0;
+      ma[r] = mom_face_flux(f, nmp_don, neg ? a_pp : a_m, neg ? a_p : a_0, neg ? a_0 : a_p, width, width_dif);
+      mb[r] = mom_face_flux(f, nmp_don, neg ? b_pp : b_m, neg ? b_p : b_0, neg ? b_0 : b_p, width, width_dif);
+      if (mine) {
+        s_ma[p] = ma[r];
+        s_mb[p] = mb[r];
+      }
+    }
+    __syncthreads();
+    // ---- C: the velocity update at sweep positions 2 .. NPS-3 ------------------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int ps = DIR == 1 ? lx : row0 + r;
+      const int j = DIR == 1 ? j0 - 2 + lx : j0 + lx;
+      const int k = DIR == 1 ? k0 + row0 + r : k0 - 2 + row0 + r;
+      if (ps >= 2 && ps <= NPS - 3 && j <= nx + 1 && k <= ny + 1) {
+        const int p = p0 + r * TX;
+        // the flux through the previous position: my own when the rows of a thread run along the sweep
+        const double ma_m = (DIR == 2 && r > 0) ? ma[r > 0 ? r - 1 : 0] : s_ma[p - SP];
+        const double mb_m = (DIR == 2 && r > 0) ? mb[r > 0 ? r - 1 : 0] : s_mb[p - SP];
+        const size_t o = idx2(pitch, j, k);
+        va_new[o] = ddiv(va0[r] * nm_pre[r] + ma_m - ma[r], np[r]);
+        vb_new[o] = ddiv(vb0[r] * nm_pre[r] + mb_m - mb[r], np[r]);
+      }
+    }
+    __syncthreads();  // stage and planes are free again
+  }
+}
+
+template <int DIR, int MS, int TX, int TY, int RPT, int STAGES, int CPS>
+static void launch_mom(const Grid& g, const MomMaps& M, const double* va_old, double* va_new, const double* vb_old,
+                       double* vb_new, const double* celld) {
+  using Cfg = MomCfg<DIR, TX, TY, RPT, STAGES, CPS>;
+  static bool configured = false;
+  if (!configured) {
+    CLV_CUDA(cudaFuncSetAttribute(advec_mom_tma_kernel<DIR, MS, TX, TY, RPT, STAGES, CPS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    configured = true;
+  }
+  const int ntx = (g.nx + 1 + Cfg::W - 1) / Cfg::W, nty = (g.ny + 1 + Cfg::H - 1) / Cfg::H;
+  const int ntiles = ntx * nty;
+  const int cap = sm_count() * CPS;
+  const int ctas = ntiles < cap ? ntiles : cap;
+  advec_mom_tma_kernel<DIR, MS, TX, TY, RPT, STAGES, CPS><<<ctas, Cfg::NT, Cfg::SMEM, stream()>>>(
+      M, va_old, va_new, vb_old, vb_new, celld, g.nx, g.ny, g.pitch, ntx, ntiles);
+}
+
+// Both velocity components of one advec_mom sweep (advec_mom_driver.f90:85,108).
+void run_advec_mom_tma(const Grid& g, int dirn, int sweep, double* vel_a, double* vel_b, double* mass_flux_x,
+                       double* vol_flux_x, double* mass_flux_y, double* vol_flux_y, double* volume, double* density1,
+                       double* celldx, double* celldy) {
+  const int mom_sweep = dirn + 2 * (sweep - 1);
+  const double* vol = dev(g, volume, CELL, IN);
+  const double* d1 = dev(g, density1, CELL, IN);
+  const double* fx = dev(g, vol_flux_x, XFACE, IN);
+  const double* fy = dev(g, vol_flux_y, YFACE, IN);
+  const double* va_old = dev(g, vel_a, VERTEX, INOUT);
+  double* va_new = dev_alt(g, vel_a, VERTEX);
+  const double* vb_old = dev(g, vel_b, VERTEX, INOUT);
+  double* vb_new = dev_alt(g, vel_b, VERTEX);
+  const double* mf = dirn == 1 ? dev(g, mass_flux_x, XFACE, IN) : dev(g, mass_flux_y, YFACE, IN);
+  const double* cd = dirn == 1 ? dev(g, celldx, X1D_CELL, IN) : dev(g, celldy, Y1D_CELL, IN);
+  // the post-volume of mom_sweep 1 needs vol_flux_y, of mom_sweep 2 vol_flux_x, of 3 and 4 neither (:69-121);
+  // the sixth box of sweeps 3/4 is loaded but never read
+  const double* in[MA_NARR] = {vol, d1, mf, va_old, vb_old, mom_sweep == 1 ? fy : fx};
+  MomMaps M;
+  LaunchScope ls(dirn == 1 ? "advec_mom_x_tma" : "advec_mom_y_tma");
+  static int cx = -1, cy = -1;
+  if (cx < 0) cx = getenv("CLOVER_B200_MX_CFG") ? atoi(getenv("CLOVER_B200_MX_CFG")) : 0;
+  if (cy < 0) cy = getenv("CLOVER_B200_MY_CFG") ? atoi(getenv("CLOVER_B200_MY_CFG")) : 0;
+#define CLV_MOM(DIR, TX, TY, RPT, ST, CPS)                                                             \
+  do {                                                                                                 \
+    using Cfg = MomCfg<DIR, TX, TY, RPT, ST, CPS>;                                                     \
+    for (int a = 0; a < MA_NARR; ++a) M.m[a] = *tensor_map_for(g, in[a], Cfg::BW, Cfg::BH);            \
+    if (mom_sweep <= 2) launch_mom<DIR, DIR, TX, TY, RPT, ST, CPS>(g, M, va_old, va_new, vb_old, vb_new, cd);     \
+    else                launch_mom<DIR, DIR + 2, TX, TY, RPT, ST, CPS>(g, M, va_old, va_new, vb_old, vb_new, cd); \
+  } while (0)
+  if (dirn == 1) {
+    switch (cx) {
+      case 1: CLV_MOM(1, 64, 4, 2, 3, 2); break;
+      case 2: CLV_MOM(1, 64, 4, 1, 2, 3); break;
+      case 3: CLV_MOM(1, 64, 4, 1, 2, 4); break;
+      case 4: CLV_MOM(1, 64, 8, 1, 2, 2); break;
+      case 5: CLV_MOM(1, 64, 2, 4, 2, 2); break;
+      default: CLV_MOM(1, 64, 4, 2, 2, 2); break;
+    }
+  } else {
+    switch (cy) {
+      case 1: CLV_MOM(2, 32, 8, 2, 2, 3); break;
+      case 2: CLV_MOM(2, 32, 8, 2, 2, 2); break;
+      case 3: CLV_MOM(2, 64, 4, 4, 2, 1); break;
+      case 4: CLV_MOM(2, 32, 16, 1, 2, 2); break;
+      case 5: CLV_MOM(2, 32, 4, 4, 2, 3); break;
+      default: CLV_MOM(2, 32, 8, 3, 2, 2); break;  // measured best on B200 (0.214 ms at 3840^2)
+    }
+  }
+#undef CLV_MOM
+  swap_alt(vel_a);
+  swap_alt(vel_b);
+}
+
+}  // namespace clv

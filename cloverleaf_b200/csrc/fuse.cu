@@ -443,6 +443,10 @@ void run_revert(const Grid& g, double* density0, double* density1, double* energ
 void run_advec_mom(const Grid& g, int dirn, int sweep, double* vel_a, double* vel_b, double* mass_flux_x,
                    double* vol_flux_x, double* mass_flux_y, double* vol_flux_y, double* volume, double* density1,
                    double* celldx, double* celldy);
+// advec_tma.cu
+void run_advec_mom_tma(const Grid& g, int dirn, int sweep, double* vel_a, double* vel_b, double* mass_flux_x,
+                       double* vol_flux_x, double* mass_flux_y, double* vol_flux_y, double* volume, double* density1,
+                       double* celldx, double* celldy);
 
 static bool same_grid(const Op& a, const Op& b) { return a.g.nx == b.g.nx && a.g.ny == b.g.ny; }
 
@@ -455,8 +459,12 @@ static size_t fuse_mom_pair(const Op* q, size_t n, size_t i) {
   for (int k = 1; k < 9; ++k)
     if (x.a[k] != y.a[k]) return 0;
   if (x.a[0] == y.a[0]) return 0;
-  // measured on B200 (profiles/): the two-component x kernel beats two launches (0.31 vs 0.40 ms at 3840^2),
-  // the two-component y march does not (register pressure), so only x sweeps are paired
+  if (tma_enabled()) {
+    run_advec_mom_tma(x.g, x.iv[2], x.iv[1], x.a[0], y.a[0], x.a[1], x.a[2], x.a[3], x.a[4], x.a[5], x.a[6], x.a[7], x.a[8]);
+    return 2;
+  }
+  // register/shuffle kernels: measured on B200 (profiles/) the two-component x kernel beats two launches (0.31 vs
+  // 0.40 ms at 3840^2), the two-component y march does not (register pressure), so only x sweeps are paired
   if (x.iv[2] != 1) return 0;
   run_advec_mom(x.g, x.iv[2], x.iv[1], x.a[0], y.a[0], x.a[1], x.a[2], x.a[3], x.a[4], x.a[5], x.a[6], x.a[7], x.a[8]);
   return 2;
