@@ -34,12 +34,20 @@ sys.path.insert(0, ROOT)
 os.environ["NCCL_DEBUG"] = os.environ.get("CLV_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
 
 ALG_BYTES_PER_CELL_STEP = 856.0  # 107 fp64 array passes
-# algorithmic array passes per launch (SURVEY.md section 8a "alg" column; advec_mom: half of the fused
-# two-component figure per single-component call)
+# Array passes per launch: (own, survey).  `own` = the fp64 array passes the kernel itself has to move (each input
+# and output field once; intermediates on chip) -- the denominator of `roofline.frac`, what ncu's dram bytes should
+# show.  `survey` = SURVEY.md section 8a "alg" passes of the reference calls the launch replaces (a fused launch
+# replaces several; their sum over a step is the fixed 107 passes = 856 B per cell-update of section 8d).
 KERNEL_PASSES = {
-    "ideal_gas": 4, "viscosity": 5, "calc_dt": 8, "pdv_predict": 11, "pdv_correct": 13, "revert": 4,
-    "accelerate": 10, "flux_calc": 8, "advec_cell_x": 7.5, "advec_cell_y": 7.5, "advec_mom_x": 4.25,
-    "advec_mom_y": 4.25, "advec_mom_x2": 8.5, "advec_mom_y2": 8.5, "reset_field": 8, "field_summary": 6,
+    "ideal_gas": (4, 4), "viscosity": (5, 5), "calc_dt": (8, 8), "pdv_predict": (11, 11), "pdv_correct": (13, 13),
+    "revert": (4, 4), "accelerate": (10, 10), "flux_calc": (8, 8), "reset_field": (8, 8), "field_summary": (6, 6),
+    "advec_cell_x": (7.5, 7.5), "advec_cell_y": (7.5, 7.5), "advec_cell_x_tma": (7.5, 7.5), "advec_cell_y_tma": (7.5, 7.5),
+    "advec_mom_x": (4.25, 4.25), "advec_mom_y": (4.25, 4.25), "advec_mom_x2": (8.5, 8.5), "advec_mom_y2": (8.5, 8.5),
+    "advec_mom_x_tma": (8.5, 8.5), "advec_mom_y_tma": (8.5, 8.5),
+    # fused launches (csrc/fuse.cu): ideal_gas+viscosity+calc_dt reads d0,e0,u0,v0,volume,xarea,yarea and writes p,q,c;
+    # PdV predictor+ideal_gas+revert reads 9 fields and writes p; accelerate+PdV corrector+flux_calc reads 9, writes 6
+    "timestep_fused": (10, 17), "timestep_tma": (10, 17), "pdv_predict_fused": (10, 19), "pdv_predict_tma": (10, 19),
+    "lagrange_correct_fused": (15, 31), "lagrange_correct_tma": (15, 31),
 }
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
@@ -301,7 +309,7 @@ def main():
     if prof:
         step_ms = sum(p["ms_total"] for p in prof.values()) / args.profile_steps
         for nm, p in sorted(prof.items(), key=lambda kv: -kv[1]["ms_total"]):
-            passes = KERNEL_PASSES.get(nm)
+            passes = KERNEL_PASSES.get(nm, (None, None))[0]
             gbs = passes * 8.0 * chunk_cells / (p["ms_avg"] * 1e-3) / 1e9 if passes else None
             kernels[nm] = dict(ms_avg=round(p["ms_avg"], 5), calls_per_step=p["calls"] / args.profile_steps,
                                share=round(p["ms_total"] / args.profile_steps / step_ms, 4),
@@ -310,8 +318,11 @@ def main():
         top = next(nm for nm in kernels if KERNEL_PASSES.get(nm))
         roofline = {"kernel": top, "bound": "hbm", "achieved": kernels[top]["alg_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": kernels[top]["frac"], "traffic": None, "peak_source": peak_src,
-                    "alg_bytes_per_launch": KERNEL_PASSES[top] * 8.0 * chunk_cells,
-                    "ms_per_launch": kernels[top]["ms_avg"]}
+                    "alg_bytes_per_launch": KERNEL_PASSES[top][0] * 8.0 * chunk_cells,
+                    "ms_per_launch": kernels[top]["ms_avg"],
+                    "reference_calls_alg_bytes_per_launch": KERNEL_PASSES[top][1] * 8.0 * chunk_cells,
+                    "note": "achieved = the launch's own compulsory bytes (each input/output field once) / mean "
+                            "launch time; the reference calls it replaces would move reference_calls_alg_bytes"}
     step_gbs = ALG_BYTES_PER_CELL_STEP * cells / world / (ms_per_step * 1e-3) / 1e9
     chunks = "%dx%d (clover_decompose)" % (d.grid()["chunk_x"], d.grid()["chunk_y"])
     d.close()

@@ -404,9 +404,20 @@ __global__ void __launch_bounds__(AMY_THREADS)
 
 namespace clv {
 
+bool tma_enabled();
+void run_advec_cell_tma(const Grid& g, int dir, int sweep, double* vertexdx, double* vertexdy, double* volume,
+                        double* density1, double* energy1, double* mass_flux_x, double* vol_flux_x, double* mass_flux_y,
+                        double* vol_flux_y);
+
 void run_advec_cell(const Grid& g, int dir, int sweep, double* vertexdx, double* vertexdy, double* volume,
                     double* density1, double* energy1, double* mass_flux_x, double* vol_flux_x,
                     double* mass_flux_y, double* vol_flux_y) {
+  // resident mode: the TMA tile kernel (advec_tma.cu); copy-in/out mode keeps the register/shuffle kernels below
+  if (tma_enabled() && is_resident() && fusion_enabled()) {
+    run_advec_cell_tma(g, dir, sweep, vertexdx, vertexdy, volume, density1, energy1, mass_flux_x, vol_flux_x,
+                       mass_flux_y, vol_flux_y);
+    return;
+  }
   const double* vol = dev(g, volume, CELL, IN);
   const double* fx = dev(g, vol_flux_x, XFACE, IN);
   const double* fy = dev(g, vol_flux_y, YFACE, IN);

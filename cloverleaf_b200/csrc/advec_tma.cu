@@ -192,6 +192,8 @@ __global__ void __launch_bounds__(TX* TY, CPS)
       const double b_m = svb[bm1], b_0 = svb[b], b_p = svb[bp1], b_pp = svb[bp2];
       va0[r] = a_0;
       vb0[r] = b_0;
+      // (the zero-numerator and inactive-limiter short cuts inside mom_face_flux skip most of the divisions on the
+      // quiescent part of the mesh; a branch-free evaluation was measured 1.5x slower on clover_bm16)
       ma[r] = mom_face_flux(f, nmp_don, neg ? a_pp : a_m, neg ? a_p : a_0, neg ? a_0 : a_p, width, width_dif);
       mb[r] = mom_face_flux(f, nmp_don, neg ? b_pp : b_m, neg ? b_p : b_0, neg ? b_0 : b_p, width, width_dif);
       if (mine) {
@@ -236,6 +238,234 @@ static void launch_mom(const Grid& g, const MomMaps& M, const double* va_old, do
   const int ctas = ntiles < cap ? ntiles : cap;
   advec_mom_tma_kernel<DIR, MS, TX, TY, RPT, STAGES, CPS><<<ctas, Cfg::NT, Cfg::SMEM, stream()>>>(
       M, va_old, va_new, vb_old, vb_new, celld, g.nx, g.ny, g.pitch, ntx, ntiles);
+}
+
+// ====================================================================================================================
+// advec_cell (advec_cell_kernel_c.c:72-177 x sweep, :182-290 y sweep).  `s` is the sweep axis, the tile owns the cells
+// s0 .. s0+NS-1 and the thread grid has N = NS+3(+1) positions along the sweep, position i <-> index s0-1+i:
+//   A  pre_vol(s)                   all positions                  (:72-102 / :182-214)
+//   B  mass_flux(s), ener_flux(s)   positions 1 .. N-1  (face s = lower face of cell s)   (:107-151 / :219-263)
+//   C  density1(s), energy1(s)      positions 1 .. NS                                      (:156-175 / :266-286)
+// mass_flux is stored for the faces of the tile's own cells; the last tile along the sweep also stores the faces
+// n+1 and n+2 (the loop of the reference runs to x_max+2 / y_max+2).
+enum { CA_VOLUME = 0, CA_VFX, CA_VFY, CA_DENSITY1, CA_ENERGY1, CA_NARR };
+
+template <int DIR, int TX, int TY, int RPT, int STAGES, int CPS>
+struct CellCfg {
+  static constexpr int NT = TX * TY;
+  static constexpr int ROWS = TY * RPT;
+  static constexpr int W = DIR == 1 ? TX - 4 : TX;      // cells per tile along x (even: TMA alignment)
+  static constexpr int H = DIR == 1 ? ROWS : ROWS - 3;  // cells per tile along y
+  static constexpr int BW = DIR == 1 ? TX + 2 : TX + 4; // box: x from j0-2
+  static constexpr int BH = DIR == 1 ? ROWS + 1 : ROWS + 2;  // box: y from k0 (x sweep) / k0-2 (y sweep)
+  static constexpr int OX = 2, OY = DIR == 1 ? 0 : 2;
+  using Ring = TileRing<CA_NARR, BW, BH, STAGES>;
+  static constexpr int NI = TX * ROWS;
+  static constexpr int SMEM = Ring::BYTES + 3 * NI * 8 + 128;
+};
+struct CellMaps {
+  CUtensorMap m[CA_NARR];
+};
+
+template <int DIR, int SWEEP, int TX, int TY, int RPT, int STAGES, int CPS>
+__global__ void __launch_bounds__(TX* TY, CPS)
+    advec_cell_tma_kernel(const __grid_constant__ CellMaps M, const double* __restrict__ d_old, double* __restrict__ d_new,
+                          const double* __restrict__ e_old, double* __restrict__ e_new,
+                          double* __restrict__ mass_flux, const double* __restrict__ vertexd, int nx, int ny, int pitch,
+                          int ntx, int nty) {
+  using Cfg = CellCfg<DIR, TX, TY, RPT, STAGES, CPS>;
+  constexpr int NT = Cfg::NT, W = Cfg::W, H = Cfg::H, BW = Cfg::BW, NI = Cfg::NI, OX = Cfg::OX, OY = Cfg::OY;
+  constexpr int NS = DIR == 1 ? W : H;             // cells of a tile along the sweep
+  constexpr int NPS = DIR == 1 ? TX : Cfg::ROWS;   // plane positions along the sweep
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = align128(smem_raw);
+  typename Cfg::Ring ring;
+  ring.init(smem);
+  double* __restrict__ s_pv = reinterpret_cast<double*>(smem + Cfg::Ring::BYTES);  // pre_vol
+  double* __restrict__ s_mf = s_pv + NI;                                           // mass flux through the lower face
+  double* __restrict__ s_ef = s_mf + NI;                                           // energy flux
+  const int tid = threadIdx.x, lx = tid % TX, ty = tid / TX;
+  const int G = gridDim.x;
+  const int ntiles = ntx * nty;
+  ring_copy(d_old, d_new, nx, ny, pitch, 0, (int)blockIdx.x * NT + tid, G * NT);
+  ring_copy(e_old, e_new, nx, ny, pitch, 0, (int)blockIdx.x * NT + tid, G * NT);
+  auto issue_tile = [&](int stage, int t) {
+    const int j0 = 1 + (t % ntx) * W, k0 = 1 + (t / ntx) * H;
+    ring.issue(M.m, stage, j0 - OX + XOFF, k0 - OY + 1);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+      const int t = (int)blockIdx.x + s * G;
+      if (t < ntiles) issue_tile(s, t);
+    }
+  }
+  constexpr int SB = DIR == 1 ? 1 : BW;  // box stride along the sweep
+  constexpr int SP = DIR == 1 ? 1 : TX;  // plane stride along the sweep
+  const int smax = (DIR == 1 ? nx : ny) + 2;
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += G, ++it) {
+    const int stage = it % STAGES;
+    if (tid == 0) {
+      const int tn = t + (STAGES - 1) * G;
+      if (tn < ntiles) issue_tile((stage + STAGES - 1) % STAGES, tn);
+    }
+    const int tx_ = t % ntx, ty_ = t / ntx;
+    const int j0 = 1 + tx_ * W, k0 = 1 + ty_ * H;
+    const bool last_along = DIR == 1 ? (tx_ == ntx - 1) : (ty_ == nty - 1);
+    const int row0 = ty * RPT;
+    // vertexdx / vertexdy at s, s-1 and min(s+1, n+2) (1-D, lower bound -1 -> index s+1); before the wait
+    double vd0[RPT], vdm[RPT], vdu[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int s_face = DIR == 1 ? j0 - 1 + lx : k0 - 1 + row0 + r;
+      const int sup = s_face + 1 < smax ? s_face + 1 : smax;  // MIN(j+1, x_max+2), :114
+      vd0[r] = vertexd[clampi(s_face, -1, smax) + 1];
+      vdm[r] = vertexd[clampi(s_face - 1, -1, smax) + 1];
+      vdu[r] = vertexd[clampi(sup, -1, smax) + 1];
+    }
+    ring.wait(stage, (uint32_t)((it / STAGES) & 1));
+    const double* __restrict__ svol = ring.tile(stage, CA_VOLUME);
+    const double* __restrict__ sfx = ring.tile(stage, CA_VFX);
+    const double* __restrict__ sfy = ring.tile(stage, CA_VFY);
+    const double* __restrict__ sd = ring.tile(stage, CA_DENSITY1);
+    const double* __restrict__ se = ring.tile(stage, CA_ENERGY1);
+    const double* __restrict__ svf = DIR == 1 ? sfx : sfy;  // the volume flux along the sweep
+    // x sweep: plane column lx <-> cell j0-1+lx (box column lx+1), plane row <-> k0+row (box row row).
+    // y sweep: plane column lx <-> cell j0+lx (box column lx+2),   plane row <-> k0-1+row (box row row+1).
+    const int b0 = DIR == 1 ? row0 * BW + lx + 1 : (row0 + 1) * BW + lx + OX;
+    const int p0 = row0 * TX + lx;
+    // ---- A: pre_vol ------------------------------------------------------------------------------------------------
+    double pv[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int c = b0 + r * BW;
+      if (DIR == 1) {
+        if (SWEEP == 1) pv[r] = svol[c] + (sfx[c + 1] - sfx[c] + sfy[c + BW] - sfy[c]);  // :77-81
+        else            pv[r] = svol[c] + sfx[c + 1] - sfx[c];                            // :94-96
+      } else {
+        if (SWEEP == 1) pv[r] = svol[c] + (sfy[c + BW] - sfy[c] + sfx[c + 1] - sfx[c]);  // :189-193
+        else            pv[r] = svol[c] + sfy[c + BW] - sfy[c];                           // :207-209
+      }
+      s_pv[p0 + r * TX] = pv[r];
+    }
+    __syncthreads();
+    // ---- B: fluxes through the lower face of position ps (valid for ps >= 1) --------------------------------------------
+    double mf[RPT], ef[RPT], vf[RPT], d0[RPT], e0[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int ps = DIR == 1 ? lx : row0 + r;
+      const int p = p0 + r * TX, b = b0 + r * BW;
+      const int s_face = DIR == 1 ? j0 - 1 + lx : k0 - 1 + row0 + r;
+      const int bm1 = b - SB, bm2 = ps >= 1 ? b - 2 * SB : b - SB;   // position 0 never stores
+      const int bup = (s_face + 1 <= smax) ? b + SB : b;            // MIN(j+1, x_max+2)
+      vf[r] = svf[b];
+      const double pv_m = s_pv[ps >= 1 ? p - SP : p];
+      const double dm2 = sd[bm2], dm1 = sd[bm1], dp1 = sd[bup];
+      const double em2 = se[bm2], em1 = se[bm1], ep1 = se[bup];
+      d0[r] = sd[b];
+      e0[r] = se[b];
+      const bool pos = vf[r] > 0.0;
+      const double pvd = pos ? pv_m : pv[r];
+      const double vdd = pos ? vdm[r] : vdu[r];
+      cell_face_flux(vf[r], pvd, pos ? dm2 : dp1, pos ? dm1 : d0[r], pos ? d0[r] : dm1, pos ? em2 : ep1,
+                     pos ? em1 : e0[r], pos ? e0[r] : em1, vd0[r], vdd, mf[r], ef[r]);
+      s_mf[p] = mf[r];
+      s_ef[p] = ef[r];
+      const int j = DIR == 1 ? j0 - 1 + lx : j0 + lx;
+      const int k = DIR == 1 ? k0 + row0 + r : k0 - 1 + row0 + r;
+      const bool cross_ok = DIR == 1 ? (k <= ny) : (j <= nx);
+      if (ps >= 1 && (ps <= NS || last_along) && s_face <= smax && cross_ok) mass_flux[idx2(pitch, j, k)] = mf[r];
+    }
+    __syncthreads();
+    // ---- C: the cell update at positions 1 .. NS -----------------------------------------------------------------------
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int ps = DIR == 1 ? lx : row0 + r;
+      const int j = DIR == 1 ? j0 - 1 + lx : j0 + lx;
+      const int k = DIR == 1 ? k0 + row0 + r : k0 - 1 + row0 + r;
+      if (ps >= 1 && ps <= NS && j <= nx && k <= ny) {
+        const int p = p0 + r * TX, b = b0 + r * BW;
+        const bool own_next = DIR == 2 && r + 1 < RPT;  // the next face along the sweep is my own next row
+        const double mf_p = own_next ? mf[r + 1 < RPT ? r + 1 : r] : s_mf[p + SP];
+        const double ef_p = own_next ? ef[r + 1 < RPT ? r + 1 : r] : s_ef[p + SP];
+        const double vf_p = own_next ? vf[r + 1 < RPT ? r + 1 : r] : svf[b + SB];
+        const double pre_mass = d0[r] * pv[r];
+        const double post_mass = pre_mass + mf[r] - mf_p;
+        const double post_ener = (e0[r] * pre_mass + ef[r] - ef_p) / post_mass;
+        const double advec_vol = pv[r] + vf[r] - vf_p;
+        const size_t o = idx2(pitch, j, k);
+        d_new[o] = post_mass / advec_vol;
+        e_new[o] = post_ener;
+      }
+    }
+    __syncthreads();  // stage and planes are free again
+  }
+}
+
+template <int DIR, int SWEEP, int TX, int TY, int RPT, int STAGES, int CPS>
+static void launch_cell(const Grid& g, const CellMaps& M, const double* d_old, double* d_new, const double* e_old,
+                        double* e_new, double* mass_flux, const double* vertexd) {
+  using Cfg = CellCfg<DIR, TX, TY, RPT, STAGES, CPS>;
+  static bool configured = false;
+  if (!configured) {
+    CLV_CUDA(cudaFuncSetAttribute(advec_cell_tma_kernel<DIR, SWEEP, TX, TY, RPT, STAGES, CPS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    configured = true;
+  }
+  const int ntx = (g.nx + Cfg::W - 1) / Cfg::W, nty = (g.ny + Cfg::H - 1) / Cfg::H;
+  const int ntiles = ntx * nty;
+  const int cap = sm_count() * CPS;
+  const int ctas = ntiles < cap ? ntiles : cap;
+  advec_cell_tma_kernel<DIR, SWEEP, TX, TY, RPT, STAGES, CPS><<<ctas, Cfg::NT, Cfg::SMEM, stream()>>>(
+      M, d_old, d_new, e_old, e_new, mass_flux, vertexd, g.nx, g.ny, g.pitch, ntx, nty);
+}
+
+void run_advec_cell_tma(const Grid& g, int dir, int sweep, double* vertexdx, double* vertexdy, double* volume,
+                        double* density1, double* energy1, double* mass_flux_x, double* vol_flux_x, double* mass_flux_y,
+                        double* vol_flux_y) {
+  const double* vol = dev(g, volume, CELL, IN);
+  const double* fx = dev(g, vol_flux_x, XFACE, IN);
+  const double* fy = dev(g, vol_flux_y, YFACE, IN);
+  const double* d_old = dev(g, density1, CELL, INOUT);
+  const double* e_old = dev(g, energy1, CELL, INOUT);
+  double* d_new = dev_alt(g, density1, CELL);
+  double* e_new = dev_alt(g, energy1, CELL);
+  const double* vd = dir == 1 ? dev(g, vertexdx, X1D_VERT, IN) : dev(g, vertexdy, Y1D_VERT, IN);
+  double* mf = dir == 1 ? dev(g, mass_flux_x, XFACE, OUT) : dev(g, mass_flux_y, YFACE, OUT);
+  const double* in[CA_NARR] = {vol, fx, fy, d_old, e_old};
+  CellMaps M;
+  static int cx = -1, cy = -1;
+  if (cx < 0) cx = getenv("CLOVER_B200_CX_CFG") ? atoi(getenv("CLOVER_B200_CX_CFG")) : 0;
+  if (cy < 0) cy = getenv("CLOVER_B200_CY_CFG") ? atoi(getenv("CLOVER_B200_CY_CFG")) : 0;
+  LaunchScope ls(dir == 1 ? "advec_cell_x_tma" : "advec_cell_y_tma");
+#define CLV_CELL(DIR, TX, TY, RPT, ST, CPS)                                                                \
+  do {                                                                                                     \
+    using Cfg = CellCfg<DIR, TX, TY, RPT, ST, CPS>;                                                        \
+    for (int a = 0; a < CA_NARR; ++a) M.m[a] = *tensor_map_for(g, in[a], Cfg::BW, Cfg::BH);                \
+    if (sweep == 1) launch_cell<DIR, 1, TX, TY, RPT, ST, CPS>(g, M, d_old, d_new, e_old, e_new, mf, vd);   \
+    else            launch_cell<DIR, 2, TX, TY, RPT, ST, CPS>(g, M, d_old, d_new, e_old, e_new, mf, vd);   \
+  } while (0)
+  if (dir == 1) {
+    switch (cx) {
+      case 1: CLV_CELL(1, 64, 4, 2, 2, 2); break;
+      case 2: CLV_CELL(1, 64, 4, 2, 3, 2); break;
+      case 3: CLV_CELL(1, 64, 4, 1, 2, 4); break;
+      case 4: CLV_CELL(1, 64, 8, 1, 2, 2); break;
+      default: CLV_CELL(1, 64, 4, 2, 2, 3); break;  // measured best on B200 (0.181 ms at 3840^2)
+    }
+  } else {
+    switch (cy) {
+      case 1: CLV_CELL(2, 32, 8, 3, 2, 2); break;
+      case 2: CLV_CELL(2, 32, 8, 2, 2, 2); break;
+      case 3: CLV_CELL(2, 32, 8, 4, 2, 2); break;
+      case 4: CLV_CELL(2, 64, 4, 3, 2, 2); break;
+      default: CLV_CELL(2, 32, 8, 2, 2, 3); break;  // measured best on B200 (0.211 ms at 3840^2)
+    }
+  }
+#undef CLV_CELL
+  swap_alt(density1);
+  swap_alt(energy1);
 }
 
 // Both velocity components of one advec_mom sweep (advec_mom_driver.f90:85,108).
