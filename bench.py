@@ -178,6 +178,21 @@ def cpu_reference_run(deck, steps, warmup, budget_s=150.0):
 
 
 def main():
+    # Libraries underneath (NCCL: "NCCL version ..." when NCCL_DEBUG is set) write to fd 1; the contract is ONE
+    # JSON line on stdout, so everything but that line goes to stderr.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(json_fd, 1)
+    if line is not None:
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -199,7 +214,7 @@ def main():
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
-            return
+            return None
         r = cpu_reference_run(deck, args.steps, args.warmup)
         line = {"impl": "reference", "metric": "cell-updates/s", "value": r["value"], "unit": "cell-updates/s",
                 "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
@@ -210,8 +225,7 @@ def main():
                                  "kind": r["kind"], "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
-        return
+        return line
 
     # ------------------------------------------------------------------ our arm (CUDA)
     import cloverleaf_b200
@@ -378,6 +392,7 @@ def main():
         cpu = {"value": r["value"], "unit": "cell-updates/s", "cores": r["cores"], "kind": r["kind"],
                "sample": r["sample"], "ms_per_step": r["ms_per_step"]}
 
+    line = None
     if rank == 0:
         line = {
             "metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": done,
@@ -394,10 +409,10 @@ def main():
                               "peak_source": peak_src},
             "kernels": kernels, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":

@@ -5,6 +5,7 @@
 #include <nccl.h>
 
 #include <cstring>
+#include <vector>
 
 #include "clover_b200.h"
 #include "common.cuh"
@@ -204,6 +205,7 @@ struct Nccl {
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
@@ -236,6 +238,7 @@ static void nccl_load() {
   LOAD(GroupStart, "ncclGroupStart");
   LOAD(GroupEnd, "ncclGroupEnd");
   LOAD(AllReduce, "ncclAllReduce");
+  LOAD(AllGather, "ncclAllGather");
   LOAD(GetErrorString, "ncclGetErrorString");
 #undef LOAD
 }
@@ -343,6 +346,275 @@ __global__ void generate_chunk_kernel(States S, int nx, int ny, int pitch, const
   if (set) { xvel0[c] = u; yvel0[c] = v; }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Halo exchange over peer memory (NVLink / NVSwitch), no library call on the data path.
+//
+// Every rank owns one device block  [512 B header | face 0 slot 0 | face 0 slot 1 | face 1 slot 0 | ...]  that its
+// four neighbours can address (cudaIpc* handles, exchanged once with ncclAllGather).  One exchange phase
+// (left/right, then bottom/top -- the reference's order, clover.f90:377-500, which is what propagates the
+// corners) is two launches:
+//   put: packs the strips of all requested fields (message layout of pack_kernel_c.c, per-field offsets of
+//        clover.f90:368-375) STRAIGHT INTO THE NEIGHBOUR's receive slot with ordinary stores through NVLink; the
+//        last CTA of a face publishes the exchange's sequence number in the neighbour's header (release, system
+//        scope);
+//   get: waits (acquire, system scope) until its own header shows that sequence number and unpacks.
+// Two slots per face, used alternately: a neighbour can only start writing exchange n+2 after it has received
+// my exchange n+1, which I sent after unpacking n (stream order), so slot n&1 is free again by then.
+struct PeerInfo {  // what a rank publishes about its block
+  cudaIpcMemHandle_t handle;
+  unsigned long long off[4];   // byte offset of slot 0 of my face f
+  unsigned long long slot[4];  // slot size in bytes
+  unsigned long long ok;
+  unsigned long long pad[7];
+};
+static_assert(sizeof(PeerInfo) == 192, "PeerInfo is exchanged as raw bytes");
+struct P2P {
+  bool tried = false, on = false;
+  unsigned char* mine = nullptr;
+  unsigned long long off[4] = {}, slot[4] = {};
+  unsigned char* peer[4] = {};            // the block of the neighbour across my face f
+  unsigned long long peer_off[4] = {}, peer_slot[4] = {};  // layout of the neighbour's face opposite to f
+  unsigned long long seq[4] = {};
+  unsigned int gen = 0;
+} PP;
+constexpr int P2P_HEADER = 512;  // flags at face*64, CTA tickets at 256 + face*64
+
+struct PhaseArgs {
+  int n;                        // faces in this phase that have a neighbour (1 or 2)
+  int face[2];
+  double* buf[2];               // put: the neighbour's slot for this exchange
+  double* mine[2];              // get: my slot
+  unsigned long long* flag_out[2];  // the neighbour's flag for its face opposite to mine
+  unsigned long long* flag_in[2];   // my flag for this face
+  unsigned long long seq[2];
+};
+
+__device__ __forceinline__ void message_index(const FieldDesc& F, int nx, int ny, int depth, int face, bool unpack,
+                                              int t, int& j, int& k, int& index, bool& valid) {
+  if (face < 2) {
+    const int span = ny + F.y_inc + 2 * depth;
+    valid = t < span * depth;
+    const int jj = t % depth + 1, kk = t / depth;
+    k = kk - depth + 1;
+    index = F.offset * depth * (ny + 5) + (jj - 1) + kk * depth;
+    if (face == 0) j = unpack ? 1 - jj : 1 + F.x_inc - 1 + jj;
+    else           j = unpack ? nx + F.x_inc + jj : nx + 1 - jj;
+  } else {
+    const int span = nx + F.x_inc + 2 * depth;
+    valid = t < span * depth;
+    const int kk = t / span + 1, jx = t % span;
+    j = jx - depth + 1;
+    index = F.offset * depth * (nx + 5) + (kk - 1) + jx * depth;
+    if (face == 2) k = unpack ? 1 - kk : 1 + F.y_inc - 1 + kk;
+    else           k = unpack ? ny + F.y_inc + kk : ny + 1 - kk;
+  }
+}
+
+// put (both faces of the phase) -> publish -> wait -> get, executed by a grid that is resident as a whole
+__device__ __forceinline__ void phase_put(const FieldTable& T, int nx, int ny, int pitch, int depth, const PhaseArgs& A,
+                                          int edge, int gtid, int gsize) {
+  const int per_field = edge * depth, per_face = per_field * T.n;
+  for (int i = gtid; i < per_face * A.n; i += gsize) {
+    const int z = i / per_face, r = i - z * per_face, f = r / per_field, t = r - f * per_field;
+    const FieldDesc& F = T.f[f];
+    int j, k, index;
+    bool valid;
+    message_index(F, nx, ny, depth, A.face[z], false, t, j, k, index, valid);
+    if (valid) A.buf[z][index] = F.p[idx2(pitch, j, k)];
+  }
+}
+__device__ __forceinline__ void phase_get(const FieldTable& T, int nx, int ny, int pitch, int depth, const PhaseArgs& A,
+                                          int edge, int gtid, int gsize) {
+  const int per_field = edge * depth, per_face = per_field * T.n;
+  for (int i = gtid; i < per_face * A.n; i += gsize) {
+    const int z = i / per_face, r = i - z * per_face, f = r / per_field, t = r - f * per_field;
+    const FieldDesc& F = T.f[f];
+    int j, k, index;
+    bool valid;
+    message_index(F, nx, ny, depth, A.face[z], true, t, j, k, index, valid);
+    if (valid) F.p[idx2(pitch, j, k)] = __ldcg(A.mine[z] + index);
+  }
+}
+// all CTAs have finished their part: the last one to arrive publishes the sequence numbers to the neighbours
+__device__ __forceinline__ void phase_publish(const PhaseArgs& A, unsigned int* ticket, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    if (atomicAdd(ticket, 1u) + 1 == target) {
+      __threadfence_system();
+      for (int z = 0; z < A.n; ++z)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.flag_out[z]), "l"(A.seq[z]) : "memory");
+    }
+  }
+}
+__device__ __forceinline__ void phase_wait(const PhaseArgs& A) {
+  if (threadIdx.x == 0) {
+    for (int z = 0; z < A.n; ++z) {
+      unsigned long long v;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(A.flag_in[z]) : "memory");
+      } while (v < A.seq[z]);
+    }
+  }
+  __syncthreads();
+}
+// grid-wide barrier (the grid is launched cooperatively: all CTAs are resident)
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*(volatile unsigned int*)counter < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// One launch per exchange: left/right phase, then bottom/top phase over the freshly received left/right halos.
+// `counters` are three monotonically increasing tickets in my header; `gen` = number of exchanges so far.
+__global__ void __launch_bounds__(256)
+    halo_exchange_kernel(FieldTable T, int nx, int ny, int pitch, int depth, PhaseArgs LR, PhaseArgs BT,
+                         unsigned int* counters, unsigned int gen) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  const unsigned int target = gen * gridDim.x;
+  if (LR.n > 0) {
+    const int edge = ny + 1 + 2 * depth;
+    phase_put(T, nx, ny, pitch, depth, LR, edge, gtid, gsize);
+    phase_publish(LR, counters + 0, target);
+    phase_wait(LR);
+    phase_get(T, nx, ny, pitch, depth, LR, edge, gtid, gsize);
+  }
+  if (BT.n > 0) {
+    // the bottom/top strips include the corner cells the left/right phase has just delivered
+    if (LR.n > 0) grid_barrier(counters + 1, target);
+    const int edge = nx + 1 + 2 * depth;
+    phase_put(T, nx, ny, pitch, depth, BT, edge, gtid, gsize);
+    phase_publish(BT, counters + 2, target);
+    phase_wait(BT);
+    phase_get(T, nx, ny, pitch, depth, BT, edge, gtid, gsize);
+  }
+}
+
+static bool p2p_setup(const Grid& g) {
+  if (PP.tried) return PP.on;
+  PP.tried = true;
+  if (const char* e = getenv("CLOVER_B200_P2P"))
+    if (atoi(e) == 0) return false;
+  const int* nb = chunk_neighbours();
+  unsigned long long bytes = P2P_HEADER;
+  for (int f = 0; f < 4; ++f) {
+    PP.slot[f] = (unsigned long long)15 * 2 * ((f < 2 ? g.ny : g.nx) + 5) * sizeof(double);
+    PP.off[f] = bytes;
+    bytes += 2 * PP.slot[f];
+  }
+  CLV_CUDA(cudaMalloc(&PP.mine, bytes));
+  CLV_CUDA(cudaMemset(PP.mine, 0, bytes));
+  PeerInfo me;
+  memset(&me, 0, sizeof(me));
+  me.ok = (cudaIpcGetMemHandle(&me.handle, PP.mine) == cudaSuccess) ? 1 : 0;
+  (void)cudaGetLastError();
+  for (int f = 0; f < 4; ++f) { me.off[f] = PP.off[f]; me.slot[f] = PP.slot[f]; }
+  // publish / collect
+  unsigned char* d_all = nullptr;
+  CLV_CUDA(cudaMalloc(&d_all, (size_t)(N.nranks + 1) * sizeof(PeerInfo)));
+  CLV_CUDA(cudaMemcpyAsync(d_all + (size_t)N.nranks * sizeof(PeerInfo), &me, sizeof(me), cudaMemcpyHostToDevice, stream()));
+  CLV_NCCL(N.AllGather(d_all + (size_t)N.nranks * sizeof(PeerInfo), d_all, sizeof(PeerInfo), ncclChar, N.comm, stream()));
+  std::vector<PeerInfo> all(N.nranks);
+  CLV_CUDA(cudaMemcpyAsync(all.data(), d_all, (size_t)N.nranks * sizeof(PeerInfo), cudaMemcpyDeviceToHost, stream()));
+  CLV_CUDA(cudaStreamSynchronize(stream()));
+  double ok = me.ok ? 1.0 : 0.0;
+  for (int f = 0; f < 4 && ok > 0; ++f) {
+    if (nb[f] == -1) continue;
+    const PeerInfo& q = all[nb[f] - 1];  // rank = chunk - 1 (clover.f90:892)
+    void* ptr = nullptr;
+    if (!q.ok || cudaIpcOpenMemHandle(&ptr, q.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      (void)cudaGetLastError();
+      ok = 0.0;
+      break;
+    }
+    PP.peer[f] = (unsigned char*)ptr;
+    PP.peer_off[f] = q.off[f ^ 1];
+    PP.peer_slot[f] = q.slot[f ^ 1];
+    if (PP.peer_slot[f] != PP.slot[f]) ok = 0.0;  // both sides of a face see the same edge length
+  }
+  // every rank must take the same path
+  CLV_CUDA(cudaMemcpyAsync(N.d_scal, &ok, sizeof(double), cudaMemcpyHostToDevice, stream()));
+  CLV_NCCL(N.AllReduce(N.d_scal, N.d_scal, 1, ncclDouble, ncclMin, N.comm, stream()));
+  CLV_CUDA(cudaMemcpyAsync(&ok, N.d_scal, sizeof(double), cudaMemcpyDeviceToHost, stream()));
+  CLV_CUDA(cudaStreamSynchronize(stream()));
+  CLV_CUDA(cudaFree(d_all));
+  PP.on = ok > 0.0;
+  if (!PP.on && N.rank == 0)
+    fprintf(stderr, "libclover_b200: peer-memory halo exchange unavailable (cudaIpc), using ncclSend/ncclRecv\n");
+  return PP.on;
+}
+
+static void p2p_release() {
+  for (int f = 0; f < 4; ++f) {
+    if (PP.peer[f]) cudaIpcCloseMemHandle(PP.peer[f]);
+    PP.peer[f] = nullptr;
+  }
+  if (PP.mine) cudaFree(PP.mine);
+  PP = P2P();
+}
+
+// the whole exchange (both phases) through peer memory: one cooperative launch
+static void p2p_exchange(const Grid& g, const HaloArgs& h) {
+  const int* nb = chunk_neighbours();
+  const FieldTable T = [&] {
+    // message offsets differ between the phases (edge length); they are recomputed in the kernel from the
+    // per-field running sum, so the table carries the offsets of BOTH: offset = index * depth * edge is applied there
+    FieldTable t;
+    t.n = 0;
+    for (int f = 0; f < 15; ++f) {
+      if (!h.fields[f]) continue;
+      FieldDesc& F = t.f[t.n];
+      F.p = dev(g, h.host[f], kFieldGeom[f].kind, INOUT_HALO);
+      F.x_inc = kFieldGeom[f].x_inc; F.y_inc = kFieldGeom[f].y_inc; F.m = kFieldGeom[f].m;
+      F.sx = kFieldGeom[f].sx; F.sy = kFieldGeom[f].sy;
+      F.offset = t.n;  // field ordinal; the kernel scales it by depth*(edge+5) per phase (clover.f90:368-375)
+      t.n++;
+    }
+    return t;
+  }();
+  if (T.n == 0) return;
+  PhaseArgs ph[2];
+  for (int phase = 0; phase < 2; ++phase) {
+    PhaseArgs& A = ph[phase];
+    A.n = 0;
+    for (int face = 2 * phase; face <= 2 * phase + 1; ++face) {
+      if (nb[face] == -1) continue;
+      const unsigned long long seq = ++PP.seq[face];
+      const int i = A.n++;
+      A.face[i] = face;
+      A.seq[i] = seq;
+      A.buf[i] = (double*)(PP.peer[face] + PP.peer_off[face] + (seq & 1) * PP.peer_slot[face]);
+      A.mine[i] = (double*)(PP.mine + PP.off[face] + (seq & 1) * PP.slot[face]);
+      A.flag_out[i] = (unsigned long long*)(PP.peer[face] + (face ^ 1) * 64);
+      A.flag_in[i] = (unsigned long long*)(PP.mine + face * 64);
+    }
+  }
+  if (ph[0].n == 0 && ph[1].n == 0) return;
+  static int ctas = 0;
+  if (!ctas) {
+    int per_sm = 0;
+    CLV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, halo_exchange_kernel, 256, 0));
+    if (per_sm < 1) fatal("halo_exchange_kernel cannot be resident");
+    int dev_id = 0, sms = 0;
+    CLV_CUDA(cudaGetDevice(&dev_id));
+    CLV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
+    ctas = sms;  // one CTA per SM is enough for <= 0.5 MB of strips and keeps the grid barrier cheap
+  }
+  unsigned int* counters = (unsigned int*)(PP.mine + 256);
+  const unsigned int gen = ++PP.gen;
+  int nx = g.nx, ny = g.ny, pitch = g.pitch, depth = h.depth;
+  FieldTable Tc = T;
+  void* args[] = {&Tc, &nx, &ny, &pitch, &depth, &ph[0], &ph[1], &counters, (void*)&gen};
+  LaunchScope ls("halo_exchange_p2p");
+  CLV_CUDA(cudaLaunchCooperativeKernel((void*)halo_exchange_kernel, dim3((unsigned)ctas), dim3(256), args, 0, stream()));
+}
+
 // ---- update_halo and the NCCL exchange on their own (host side) ---------------------------------------
 static FieldTable field_table(const Grid& g, const HaloArgs& h, int depth, int edge) {
   FieldTable T;
@@ -384,6 +656,10 @@ void run_update_halo(const Grid& g, const HaloArgs& h) {
 void run_exchange(const Grid& g, const HaloArgs& h) {
   const int* nb = chunk_neighbours();
   const int depth = h.depth;
+  if (p2p_setup(g)) {
+    p2p_exchange(g, h);
+    return;
+  }
   for (int phase = 0; phase < 2; ++phase) {
     const int fa = phase * 2, fb = fa + 1;
     if (nb[fa] == -1 && nb[fb] == -1) continue;
@@ -483,6 +759,7 @@ void clover_b200_comm_init_(int* nranks, int* rank, char* id128) {
 }
 
 void clover_b200_comm_finalize_internal() {
+  p2p_release();
   if (N.comm) {
     N.CommDestroy(N.comm);
     N.comm = nullptr;
