@@ -58,7 +58,7 @@ def build_b200(force=False, verbose=False):
         return LIB_B200
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     cus = [s for s in srcs if s.endswith(".cu")]
-    cmd = [nvcc] + NVCC_FLAGS + ["--threads", "4", "-I/usr/include"] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_B200] + sorted(cus) + ["-ldl"]
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("CLV_NVCC_EXTRA", "").split() + ["--threads", "4", "-I/usr/include"] + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_B200] + sorted(cus) + ["-ldl"]
     out = _run(cmd)
     if verbose:
         print(out)

@@ -109,6 +109,104 @@ __global__ void __launch_bounds__(BX* BY)
   block_reduce_publish<1, true>(m, partials, ticket, out, P.g_big);
 }
 
+// ---- T with TMA tile staging (tma.cuh): persistent CTAs of 32x8 threads, one cell per thread, the seven input
+// fields of a 32x8 tile arrive as 36x10 boxes with corner (j0-2, k0-1).  Same arithmetic as timestep_kernel.
+constexpr int TT_W = BX, TT_H = BY, TT_BW = TT_W + 4, TT_BH = TT_H + 2, TT_NARR = 7, TT_STAGES = 4;
+enum { TA_D0 = 0, TA_E0, TA_U0, TA_V0, TA_VOL, TA_XA, TA_YA };
+using TimestepRing = TileRing<TT_NARR, TT_BW, TT_BH, TT_STAGES>;
+constexpr int TT_SMEM = TimestepRing::BYTES + 128;
+struct TimestepMaps {
+  CUtensorMap m[TT_NARR];
+};
+
+template <bool WRITE_SS>
+__global__ void __launch_bounds__(BX* BY, 2)
+    timestep_tma_kernel(const __grid_constant__ TimestepMaps M, DtParams P, const double* __restrict__ celldx,
+                        const double* __restrict__ celldy, const double* __restrict__ density0,
+                        const double* __restrict__ energy0, double* __restrict__ pressure,
+                        double* __restrict__ viscosity, double* __restrict__ soundspeed, double* __restrict__ partials,
+                        unsigned int* ticket, double* __restrict__ out, int nx, int ny, int pitch, int ntx, int ntiles) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = align128(smem_raw);
+  TimestepRing ring;
+  ring.init(smem);
+  const int lx = threadIdx.x, ly = threadIdx.y;
+  const bool leader = (lx == 0 && ly == 0);
+  const int G = gridDim.x;
+  double m[1] = {P.g_big};
+  auto issue_tile = [&](int stage, int t) {
+    const int j0 = 1 + (t % ntx) * TT_W, k0 = 1 + (t / ntx) * TT_H;
+    ring.issue(M.m, stage, j0 - 2 + XOFF, k0 - 1 + 1);
+  };
+  if (leader) {
+#pragma unroll
+    for (int s = 0; s < TT_STAGES - 1; ++s) {
+      const int t = (int)blockIdx.x + s * G;
+      if (t < ntiles) issue_tile(s, t);
+    }
+  }
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += G, ++it) {
+    const int stage = it % TT_STAGES;
+    if (leader) {
+      const int tn = t + (TT_STAGES - 1) * G;
+      if (tn < ntiles) issue_tile((stage + TT_STAGES - 1) % TT_STAGES, tn);
+    }
+    const int j = 1 + (t % ntx) * TT_W + lx, k = 1 + (t / ntx) * TT_H + ly;
+    const bool active = j <= nx && k <= ny;
+    const int jc = j <= nx ? j : nx, kc = k <= ny ? k : ny;  // 1-D geometry of the threads beyond the chunk
+    const double dsx = celldx[jc + 1], dsy = celldy[kc + 1], dsx1 = celldx[jc + 2], dsy1 = celldy[kc + 2];
+    ring.wait(stage, (uint32_t)((it / TT_STAGES) & 1));
+    const double* __restrict__ sd = ring.tile(stage, TA_D0);
+    const double* __restrict__ se = ring.tile(stage, TA_E0);
+    const double* __restrict__ su = ring.tile(stage, TA_U0);
+    const double* __restrict__ sv = ring.tile(stage, TA_V0);
+    const double* __restrict__ svol = ring.tile(stage, TA_VOL);
+    const double* __restrict__ sxa = ring.tile(stage, TA_XA);
+    const double* __restrict__ sya = ring.tile(stage, TA_YA);
+    const int b = (ly + 1) * TT_BW + lx + 2;
+    const double rho = sd[b], en = se[b];
+    const double rl = sd[b - 1], rr = sd[b + 1], rb = sd[b - TT_BW], rt = sd[b + TT_BW];
+    const double el = se[b - 1], er = se[b + 1], eb = se[b - TT_BW], et = se[b + TT_BW];
+    const double u00 = su[b], u10 = su[b + 1], u01 = su[b + TT_BW], u11 = su[b + TT_BW + 1];
+    const double v00 = sv[b], v10 = sv[b + 1], v01 = sv[b + TT_BW], v11 = sv[b + TT_BW + 1];
+    const double vol = svol[b];
+    const double xa0 = sxa[b], xa1 = sxa[b + 1], ya0 = sya[b], ya1 = sya[b + TT_BW];
+    __syncthreads();  // everything this tile needs is in registers: the stage can be refilled
+    // ideal_gas_kernel_c.c:52 for the four neighbours
+    const double pl = (1.4 - 1.0) * rl * el, pr = (1.4 - 1.0) * rr * er;
+    const double pb = (1.4 - 1.0) * rb * eb, pt = (1.4 - 1.0) * rt * et;
+    ViscIn V{u00, u10, u01, u11, v00, v10, v01, v11, dsx, dsy, dsx1, dsy1, pl, pr, pb, pt, rho};
+    DtIn D{dsx, dsy, vol, 0.0, 0.0, rho, u00, u10, u01, u11, v00, v10, v01, v11, xa0, xa1, ya0, ya1};
+    if (active) {
+      bool bad = false;
+      double p, ss, q;
+      double cell_dt = timestep_cell<false>(rho, en, V, D, P, p, ss, q, bad);
+      if (bad) cell_dt = timestep_cell<true>(rho, en, V, D, P, p, ss, q, bad);
+      const size_t c = idx2(pitch, j, k);
+      pressure[c] = p;
+      viscosity[c] = q;
+      if (WRITE_SS) soundspeed[c] = ss;
+      if (cell_dt < m[0]) m[0] = cell_dt;
+      // depth-1 halo ring of pressure (corners by the corner cells)
+      const bool L = (j == 1), R_ = (j == nx), B = (k == 1), T = (k == ny);
+      if (L) pressure[c - 1] = pl;
+      if (R_) pressure[c + 1] = pr;
+      if (B) pressure[c - pitch] = pb;
+      if (T) pressure[c + pitch] = pt;
+      if ((L || R_) && (B || T)) {
+        const size_t cc = c + (L ? -1 : 1) + (B ? -(ptrdiff_t)pitch : (ptrdiff_t)pitch);
+        pressure[cc] = (1.4 - 1.0) * density0[cc] * energy0[cc];
+        // a one-cell-wide or one-cell-high chunk: the same cell is on both rims
+        if (L && R_) { const size_t c2 = c + 1 + (B ? -(ptrdiff_t)pitch : (ptrdiff_t)pitch); pressure[c2] = (1.4 - 1.0) * density0[c2] * energy0[c2]; }
+        if (B && T) { const size_t c2 = c + (L ? -1 : 1) + (ptrdiff_t)pitch; pressure[c2] = (1.4 - 1.0) * density0[c2] * energy0[c2]; }
+        if (L && R_ && B && T) { const size_t c2 = c + 1 + (ptrdiff_t)pitch; pressure[c2] = (1.4 - 1.0) * density0[c2] * energy0[c2]; }
+      }
+    }
+  }
+  block_reduce_publish<1, true>(m, partials, ticket, out, P.g_big);
+}
+
 // ================================================================================================
 // P: PdV predictor (PdV_kernel_c.c:63-113) + ideal_gas on the predicted state (ideal_gas_kernel_c.c:48-59).
 // The predicted density1/energy1 are not stored: revert (revert_kernel_c.c:46-62) replaces them right after.
@@ -152,6 +250,88 @@ __global__ void __launch_bounds__(BX* BY)
       if (WRITE_SS) soundspeed[c] = ss;
     }
   CLV_ROWS_END
+}
+
+// ---- P with TMA tile staging: 32x8 threads, one cell per thread, nine 34x9 boxes with corner (j0, k0) ------------
+constexpr int PT_W = BX, PT_H = BY, PT_BW = PT_W + 2, PT_BH = PT_H + 1, PT_NARR = 9;
+// measured on B200 at 3840^2: (stages, CTAs/SM) = (4,2) 0.202 ms, (2,4) 0.217, (3,3) 0.228
+#ifndef PT_STAGES
+#define PT_STAGES 4
+#endif
+#ifndef PT_CPS
+#define PT_CPS 2
+#endif
+enum { PA_XAREA = 0, PA_YAREA, PA_VOLUME, PA_DENSITY0, PA_ENERGY0, PA_PRESSURE, PA_VISCOSITY, PA_XVEL0, PA_YVEL0 };
+using PredictRing = TileRing<PT_NARR, PT_BW, PT_BH, PT_STAGES>;
+constexpr int PT_SMEM = PredictRing::BYTES + 128;
+struct PredictMaps {
+  CUtensorMap m[PT_NARR];
+};
+
+template <bool WRITE_SS>
+__global__ void __launch_bounds__(BX* BY, PT_CPS)
+    pdv_predict_eos_tma_kernel(const __grid_constant__ PredictMaps M, double dt, double* __restrict__ pressure,
+                               double* __restrict__ soundspeed, int nx, int ny, int pitch, int ntx, int ntiles) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = align128(smem_raw);
+  PredictRing ring;
+  ring.init(smem);
+  const int lx = threadIdx.x, ly = threadIdx.y;
+  const bool leader = (lx == 0 && ly == 0);
+  const int G = gridDim.x;
+  auto issue_tile = [&](int stage, int t) {
+    const int j0 = 1 + (t % ntx) * PT_W, k0 = 1 + (t / ntx) * PT_H;
+    ring.issue(M.m, stage, j0 + XOFF, k0 + 1);
+  };
+  if (leader) {
+#pragma unroll
+    for (int s = 0; s < PT_STAGES - 1; ++s) {
+      const int t = (int)blockIdx.x + s * G;
+      if (t < ntiles) issue_tile(s, t);
+    }
+  }
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += G, ++it) {
+    const int stage = it % PT_STAGES;
+    if (leader) {
+      const int tn = t + (PT_STAGES - 1) * G;
+      if (tn < ntiles) issue_tile((stage + PT_STAGES - 1) % PT_STAGES, tn);
+    }
+    const int j = 1 + (t % ntx) * PT_W + lx, k = 1 + (t / ntx) * PT_H + ly;
+    ring.wait(stage, (uint32_t)((it / PT_STAGES) & 1));
+    const double* __restrict__ sxa = ring.tile(stage, PA_XAREA);
+    const double* __restrict__ sya = ring.tile(stage, PA_YAREA);
+    const double* __restrict__ sx = ring.tile(stage, PA_XVEL0);
+    const double* __restrict__ sy = ring.tile(stage, PA_YVEL0);
+    const int b = ly * PT_BW + lx;
+    const double x00 = sx[b], x10 = sx[b + 1], x01 = sx[b + PT_BW], x11 = sx[b + PT_BW + 1];
+    const double y00 = sy[b], y10 = sy[b + 1], y01 = sy[b + PT_BW], y11 = sy[b + PT_BW + 1];
+    const double vol = ring.tile(stage, PA_VOLUME)[b], rho0 = ring.tile(stage, PA_DENSITY0)[b];
+    const double pres = ring.tile(stage, PA_PRESSURE)[b], visc = ring.tile(stage, PA_VISCOSITY)[b];
+    const double en0 = ring.tile(stage, PA_ENERGY0)[b];
+    const double xa0 = sxa[b], xa1 = sxa[b + 1], ya0 = sya[b], ya1 = sya[b + PT_BW];
+    __syncthreads();  // everything this tile needs is in registers: the stage can be refilled
+    if (j <= nx && k <= ny) {
+      // PdV_kernel_c.c:63-113 (predictor), ideal_gas_kernel_c.c:48-59 on the predicted state
+      const double left = xa0 * (x00 + x01 + x00 + x01) * 0.25 * dt * 0.5;
+      const double right = xa1 * (x10 + x11 + x10 + x11) * 0.25 * dt * 0.5;
+      const double bottom = ya0 * (y00 + y10 + y00 + y10) * 0.25 * dt * 0.5;
+      const double top = ya1 * (y01 + y11 + y01 + y11) * 0.25 * dt * 0.5;
+      const double total = right - left + top - bottom;
+      const double vc = vol / (vol + total);
+      const double recip = 1.0 / vol;
+      const double de = (pres / rho0 + ddiv(visc, rho0)) * total * recip;
+      const double e1 = en0 - de;
+      const double d1 = rho0 * vc;
+      bool bad = false;
+      double p, ss;
+      ideal_gas_cell<false>(d1, e1, p, ss, bad);
+      if (bad) ideal_gas_cell<true>(d1, e1, p, ss, bad);
+      const size_t c = idx2(pitch, j, k);
+      pressure[c] = p;
+      if (WRITE_SS) soundspeed[c] = ss;
+    }
+  }
 }
 
 // ================================================================================================
@@ -583,11 +763,30 @@ static size_t fuse_timestep(const Op* q, size_t n, size_t i) {
                                                              BX * BY, 0));
       if (g_ctas_per_sm_timestep[0] < 1) g_ctas_per_sm_timestep[0] = 1;
     }
+    if (tma_enabled()) {
+      static bool configured = false;
+      if (!configured) {
+        CLV_CUDA(cudaFuncSetAttribute(timestep_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM));
+        configured = true;
+      }
+      TimestepMaps M;
+      const double* in[TT_NARR] = {d0, e0, xv, yv, vol, xa, ya};
+      for (int a = 0; a < TT_NARR; ++a) M.m[a] = *tensor_map_for(g, in[a], TT_BW, TT_BH);
+      const int ntx = (g.nx + TT_W - 1) / TT_W, nty = (g.ny + TT_H - 1) / TT_H;
+      const int ntiles = ntx * nty;
+      const int cap = sm_count() * 2;
+      const int ctas = ntiles < cap ? ntiles : cap;
+      double* part = partials((size_t)ctas);
+      LaunchScope ls("timestep_tma");
+      timestep_tma_kernel<true><<<ctas, dim3(BX, BY), TT_SMEM, stream()>>>(M, P, cdx, cdy, d0, e0, p, qv, ss, part, ticket(),
+                                                                          host_scalars(), g.nx, g.ny, g.pitch, ntx, ntiles);
+    } else {
     const dim3 grid = persistent_grid(r, 1, g_ctas_per_sm_timestep[0]);
     double* part = partials((size_t)grid.x * grid.y);
     LaunchScope ls("timestep_fused");
     timestep_kernel<true><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, P, xa, ya, cdx, cdy, vol, d0, e0, p, qv, ss,
                                                                xv, yv, part, ticket(), host_scalars());
+    }
   }
   if (ex2) run_exchange(g, halo_args(*ex2, -1));
   if (uh2) run_update_halo(g, halo_args(*uh2, -1));
@@ -626,6 +825,26 @@ static size_t fuse_predict(const Op* q, size_t n, size_t i) {
     double* ss = dev(g, soundspeed, CELL, OUT);
     const double* x0 = dev(g, xvel0, VERTEX, IN);
     const double* y0 = dev(g, yvel0, VERTEX, IN);
+    if (tma_enabled()) {
+      static bool configured = false;
+      if (!configured) {
+        CLV_CUDA(cudaFuncSetAttribute(pdv_predict_eos_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
+        CLV_CUDA(cudaFuncSetAttribute(pdv_predict_eos_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
+        configured = true;
+      }
+      PredictMaps M;
+      const double* in[PT_NARR] = {xa, ya, vol, d0, e0, p, qv, x0, y0};
+      for (int a = 0; a < PT_NARR; ++a) M.m[a] = *tensor_map_for(g, in[a], PT_BW, PT_BH);
+      const int ntx = (g.nx + PT_W - 1) / PT_W, nty = (g.ny + PT_H - 1) / PT_H;
+      const int ntiles = ntx * nty;
+      const int cap = sm_count() * PT_CPS;
+      const int ctas = ntiles < cap ? ntiles : cap;
+      LaunchScope ls("pdv_predict_tma");
+      if (write_ss)
+        pdv_predict_eos_tma_kernel<true><<<ctas, dim3(BX, BY), PT_SMEM, stream()>>>(M, pv.sv[0], p, ss, g.nx, g.ny, g.pitch, ntx, ntiles);
+      else
+        pdv_predict_eos_tma_kernel<false><<<ctas, dim3(BX, BY), PT_SMEM, stream()>>>(M, pv.sv[0], p, ss, g.nx, g.ny, g.pitch, ntx, ntiles);
+    } else {
     const Range r = make_range(1, g.nx, 1, g.ny);
     const dim3 grid = grid_for(r, NR_PRED);
     LaunchScope ls("pdv_predict_fused");
@@ -635,6 +854,7 @@ static size_t fuse_predict(const Op* q, size_t n, size_t i) {
     else
       pdv_predict_eos_kernel<false><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, pv.sv[0], xa, ya, vol, d0, e0, p,
                                                                          qv, ss, x0, y0);
+    }
   }
   if (ex) run_exchange(g, halo_args(*ex, -1));
   if (uh) run_update_halo(g, halo_args(*uh, -1));
