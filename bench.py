@@ -330,8 +330,16 @@ def _main():
                                alg_gbs=round(gbs, 1) if gbs else None,
                                frac=round(gbs / peak, 4) if gbs else None)
         top = next(nm for nm in kernels if KERNEL_PASSES.get(nm))
+        # dram bytes per launch of the same kernel from the committed ncu capture (same workload, 1 GPU), else null
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if world == 1 and tj.get("workload", "").startswith(workload):
+                traffic = tj["bytes_per_launch"].get(top)
+        except Exception:
+            traffic = None
         roofline = {"kernel": top, "bound": "hbm", "achieved": kernels[top]["alg_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kernels[top]["frac"], "traffic": None, "peak_source": peak_src,
+                    "frac": kernels[top]["frac"], "traffic": traffic, "peak_source": peak_src,
                     "alg_bytes_per_launch": KERNEL_PASSES[top][0] * 8.0 * chunk_cells,
                     "ms_per_launch": kernels[top]["ms_avg"],
                     "reference_calls_alg_bytes_per_launch": KERNEL_PASSES[top][1] * 8.0 * chunk_cells,

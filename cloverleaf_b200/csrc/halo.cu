@@ -360,6 +360,9 @@ __global__ void generate_chunk_kernel(States S, int nx, int ny, int pitch, const
 //   get: waits (acquire, system scope) until its own header shows that sequence number and unpacks.
 // Two slots per face, used alternately: a neighbour can only start writing exchange n+2 after it has received
 // my exchange n+1, which I sent after unpacking n (stream order), so slot n&1 is free again by then.
+constexpr int P2P_MAX_RANKS = 64;
+constexpr int AR_OFF = 1024, AR_SLOT = 128;  // all-reduce mailboxes: [parity][sender rank] x {8 values, sequence number}
+constexpr int P2P_HEADER = AR_OFF + 2 * P2P_MAX_RANKS * AR_SLOT;  // flags at face*64, tickets at 256, mailboxes at 1024
 struct PeerInfo {  // what a rank publishes about its block
   cudaIpcMemHandle_t handle;
   unsigned long long off[4];   // byte offset of slot 0 of my face f
@@ -376,8 +379,10 @@ struct P2P {
   unsigned long long peer_off[4] = {}, peer_slot[4] = {};  // layout of the neighbour's face opposite to f
   unsigned long long seq[4] = {};
   unsigned int gen = 0;
+  unsigned char* all[P2P_MAX_RANKS] = {};  // every rank's block (mine included)
+  unsigned char** d_all = nullptr;         // the same table on the device
+  unsigned long long ar_seq = 0;
 } PP;
-constexpr int P2P_HEADER = 512;  // flags at face*64, CTA tickets at 256 + face*64
 
 struct PhaseArgs {
   int n;                        // faces in this phase that have a neighbour (1 or 2)
@@ -523,20 +528,28 @@ static bool p2p_setup(const Grid& g) {
   std::vector<PeerInfo> all(N.nranks);
   CLV_CUDA(cudaMemcpyAsync(all.data(), d_all, (size_t)N.nranks * sizeof(PeerInfo), cudaMemcpyDeviceToHost, stream()));
   CLV_CUDA(cudaStreamSynchronize(stream()));
-  double ok = me.ok ? 1.0 : 0.0;
-  for (int f = 0; f < 4 && ok > 0; ++f) {
-    if (nb[f] == -1) continue;
-    const PeerInfo& q = all[nb[f] - 1];  // rank = chunk - 1 (clover.f90:892)
+  double ok = (me.ok && N.nranks <= P2P_MAX_RANKS) ? 1.0 : 0.0;
+  for (int r = 0; r < N.nranks && ok > 0; ++r) {
+    if (r == N.rank) { PP.all[r] = PP.mine; continue; }
     void* ptr = nullptr;
-    if (!q.ok || cudaIpcOpenMemHandle(&ptr, q.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    if (!all[r].ok || cudaIpcOpenMemHandle(&ptr, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
       (void)cudaGetLastError();
       ok = 0.0;
       break;
     }
-    PP.peer[f] = (unsigned char*)ptr;
+    PP.all[r] = (unsigned char*)ptr;
+  }
+  for (int f = 0; f < 4 && ok > 0; ++f) {
+    if (nb[f] == -1) continue;
+    const PeerInfo& q = all[nb[f] - 1];  // rank = chunk - 1 (clover.f90:892)
+    PP.peer[f] = PP.all[nb[f] - 1];
     PP.peer_off[f] = q.off[f ^ 1];
     PP.peer_slot[f] = q.slot[f ^ 1];
     if (PP.peer_slot[f] != PP.slot[f]) ok = 0.0;  // both sides of a face see the same edge length
+  }
+  if (ok > 0) {
+    CLV_CUDA(cudaMalloc(&PP.d_all, sizeof(PP.all)));
+    CLV_CUDA(cudaMemcpyAsync(PP.d_all, PP.all, sizeof(PP.all), cudaMemcpyHostToDevice, stream()));
   }
   // every rank must take the same path
   CLV_CUDA(cudaMemcpyAsync(N.d_scal, &ok, sizeof(double), cudaMemcpyHostToDevice, stream()));
@@ -551,12 +564,44 @@ static bool p2p_setup(const Grid& g) {
 }
 
 static void p2p_release() {
-  for (int f = 0; f < 4; ++f) {
-    if (PP.peer[f]) cudaIpcCloseMemHandle(PP.peer[f]);
-    PP.peer[f] = nullptr;
-  }
+  for (int r = 0; r < P2P_MAX_RANKS; ++r)
+    if (PP.all[r] && PP.all[r] != PP.mine) cudaIpcCloseMemHandle(PP.all[r]);
+  if (PP.d_all) cudaFree(PP.d_all);
   if (PP.mine) cudaFree(PP.mine);
   PP = P2P();
+}
+
+// All-reduce of up to 8 doubles over peer memory: every rank drops its values, then the sequence number (release,
+// system scope), into its mailbox in every rank's block; thread r of the single CTA waits for rank r's mailbox and
+// thread 0 folds the values in rank order, so all ranks compute bit-identical results (clover_min: clover.f90:
+// 532-551 MPI_ALLREDUCE(MIN); clover_sum: :506-525).  `in`/`out` are pinned, device-visible host memory.
+__global__ void __launch_bounds__(P2P_MAX_RANKS)
+    p2p_allreduce_kernel(unsigned char** all, int nranks, int rank, const double* in, double* out, int n, int is_min,
+                         unsigned long long seq) {
+  __shared__ double v[P2P_MAX_RANKS][8];
+  const int r = threadIdx.x;
+  const size_t box = AR_OFF + (size_t)(seq & 1) * P2P_MAX_RANKS * AR_SLOT;
+  if (r < nranks) {
+    double* dst = reinterpret_cast<double*>(all[r] + box + (size_t)rank * AR_SLOT);
+    for (int i = 0; i < n; ++i) dst[i] = in[i];
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst + 8), "l"(seq) : "memory");
+    const double* src = reinterpret_cast<const double*>(all[rank] + box + (size_t)r * AR_SLOT);
+    unsigned long long s;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(s) : "l"(src + 8) : "memory");
+    } while (s < seq);
+    for (int i = 0; i < n; ++i) v[r][i] = __ldcg(src + i);
+  }
+  __syncthreads();
+  if (r == 0) {
+    for (int i = 0; i < n; ++i) {
+      double a = v[0][i];
+      for (int q = 1; q < nranks; ++q) a = is_min ? ((v[q][i] < a) ? v[q][i] : a) : a + v[q][i];
+      out[i] = a;
+    }
+    __threadfence_system();
+  }
 }
 
 // the whole exchange (both phases) through peer memory: one cooperative launch
@@ -805,6 +850,21 @@ static void allreduce_host(double* values, int n, ncclRedOp_t op) {
   flush_deferred();
   if (!N.comm || N.nranks == 1) return;
   if (n > 16) fatal("allreduce of %d values (max 16)", n);
+  if (n <= 8 && chunk_registered()) {
+    int one = 1, nx = chunk_nx(), ny = chunk_ny();
+    if (p2p_setup(grid_of_noflush(&one, &nx, &one, &ny))) {
+      double* h = host_scalars();  // pinned + mapped: [16..23] in, [24..31] out
+      for (int i = 0; i < n; ++i) h[16 + i] = values[i];
+      {
+        LaunchScope ls("allreduce_p2p");
+        p2p_allreduce_kernel<<<1, P2P_MAX_RANKS, 0, stream()>>>(PP.d_all, N.nranks, N.rank, h + 16, h + 24, n,
+                                                               op == ncclMin ? 1 : 0, ++PP.ar_seq);
+      }
+      CLV_CUDA(cudaStreamSynchronize(stream()));
+      for (int i = 0; i < n; ++i) values[i] = h[24 + i];
+      return;
+    }
+  }
   CLV_CUDA(cudaMemcpyAsync(N.d_scal, values, n * sizeof(double), cudaMemcpyHostToDevice, stream()));
   CLV_NCCL(N.AllReduce(N.d_scal, N.d_scal, (size_t)n, ncclDouble, op, N.comm, stream()));
   CLV_CUDA(cudaMemcpyAsync(values, N.d_scal, n * sizeof(double), cudaMemcpyDeviceToHost, stream()));
