@@ -741,8 +741,12 @@ static size_t fuse_timestep(const Op* q, size_t n, size_t i) {
   double *xarea = dt.a[0], *yarea = dt.a[1], *volume = dt.a[4];
 
   // halos of density0, energy0, xvel0, yvel0 first (pressure's ring is produced by the kernel itself)
-  if (ex1) run_exchange(g, halo_args(*ex1, F_PRESSURE));
-  if (uh1) run_update_halo(g, halo_args(*uh1, F_PRESSURE));
+  {
+    HaloArgs hx, hu;
+    if (ex1) hx = halo_args(*ex1, F_PRESSURE);
+    if (uh1) hu = halo_args(*uh1, F_PRESSURE);
+    run_exchange_then_halo(g, ex1 ? &hx : nullptr, uh1 ? &hu : nullptr);
+  }
   {
     const double* xa = dev(g, xarea, XFACE, IN);
     const double* ya = dev(g, yarea, YFACE, IN);
@@ -788,8 +792,12 @@ static size_t fuse_timestep(const Op* q, size_t n, size_t i) {
                                                                xv, yv, part, ticket(), host_scalars());
     }
   }
-  if (ex2) run_exchange(g, halo_args(*ex2, -1));
-  if (uh2) run_update_halo(g, halo_args(*uh2, -1));
+  {
+    HaloArgs hx, hu;
+    if (ex2) hx = halo_args(*ex2, -1);
+    if (uh2) hu = halo_args(*uh2, -1);
+    run_exchange_then_halo(g, ex2 ? &hx : nullptr, uh2 ? &hu : nullptr);
+  }
   return k - i;
 }
 
@@ -856,8 +864,12 @@ static size_t fuse_predict(const Op* q, size_t n, size_t i) {
                                                                          qv, ss, x0, y0);
     }
   }
-  if (ex) run_exchange(g, halo_args(*ex, -1));
-  if (uh) run_update_halo(g, halo_args(*uh, -1));
+  {
+    HaloArgs hx, hu;
+    if (ex) hx = halo_args(*ex, -1);
+    if (uh) hu = halo_args(*uh, -1);
+    run_exchange_then_halo(g, ex ? &hx : nullptr, uh ? &hu : nullptr);
+  }
   run_revert(g, density0, density1, energy0, energy1);  // a lazy copy in resident mode
   return k - i;
 }
@@ -916,8 +928,17 @@ static size_t fuse_correct(const Op* q, size_t n, size_t i) {
   return 3;
 }
 
+// ---- X: clover_exchange -> update_halo_kernel with the same field list -------------------------------------------------
+static size_t fuse_exchange_halo(const Op* q, size_t n, size_t i) {
+  if (i + 1 >= n || q[i].kind != OP_EXCHANGE || q[i + 1].kind != OP_UPDATE_HALO || !same_grid(q[i], q[i + 1])) return 0;
+  const HaloArgs hx = halo_args(q[i], -1), hu = halo_args(q[i + 1], -1);
+  run_exchange_then_halo(q[i].g, &hx, &hu);
+  return 2;
+}
+
 size_t fuse_at(const Op* q, size_t n, size_t i) {
   switch (q[i].kind) {
+    case OP_EXCHANGE: return fuse_exchange_halo(q, n, i);
     case OP_ADVEC_MOM: return fuse_mom_pair(q, n, i);
     case OP_IDEAL_GAS: return fuse_timestep(q, n, i);
     case OP_PDV_PREDICT: return fuse_predict(q, n, i);

@@ -60,14 +60,11 @@ static const struct { int x_inc, y_inc, m; double sx, sy; Kind kind; } kFieldGeo
 // (halo data received from a neighbour chunk).  Mirror rules:
 //     bottom: 1-k <- m+k         top:   ny+y_inc+k <- ny+y_inc+(1-m)-k
 //     left:   1-j <- m+j         right: nx+x_inc+j <- nx+x_inc+(1-m)-j
-__global__ void __launch_bounds__(256)
-    update_halo_kernel(FieldTable T, int nx, int ny, int pitch, int depth, int ext_left, int ext_right,
-                       int ext_bottom, int ext_top) {
-  const FieldDesc F = T.f[blockIdx.y];
+__device__ __forceinline__ void update_halo_item(const FieldDesc& F, int nx, int ny, int pitch, int depth, int ext_left,
+                                                 int ext_right, int ext_bottom, int ext_top, int t) {
   const int W = nx + F.x_inc + 2 * depth;  // width of the bottom/top strips (corners included)
   const int H = ny + F.y_inc;              // height of the left/right strips (corners excluded)
   const int n_bt = 2 * depth * W, n_lr = 2 * depth * H;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_bt + n_lr) return;
   int jd, kd;
   if (t < n_bt) {
@@ -94,6 +91,12 @@ __global__ void __launch_bounds__(256)
     sign = sign * F.sy;
   }
   F.p[idx2(pitch, jd, kd)] = sign * F.p[idx2(pitch, js, ks)];
+}
+__global__ void __launch_bounds__(256)
+    update_halo_kernel(FieldTable T, int nx, int ny, int pitch, int depth, int ext_left, int ext_right,
+                       int ext_bottom, int ext_top) {
+  update_halo_item(T.f[blockIdx.y], nx, ny, pitch, depth, ext_left, ext_right, ext_bottom, ext_top,
+                   (int)(blockIdx.x * blockDim.x + threadIdx.x));
 }
 
 // Chunks narrower than depth+1 cells: the mirror source of a depth-2 halo cell can itself be a halo cell that an
@@ -378,7 +381,7 @@ struct P2P {
   unsigned char* peer[4] = {};            // the block of the neighbour across my face f
   unsigned long long peer_off[4] = {}, peer_slot[4] = {};  // layout of the neighbour's face opposite to f
   unsigned long long seq[4] = {};
-  unsigned int gen = 0;
+  unsigned int gen = 0, gen_bc = 0;  // exchange launches so far / of those, the ones that also did the boundary
   unsigned char* all[P2P_MAX_RANKS] = {};  // every rank's block (mine included)
   unsigned char** d_all = nullptr;         // the same table on the device
   unsigned long long ar_seq = 0;
@@ -480,7 +483,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 // `counters` are three monotonically increasing tickets in my header; `gen` = number of exchanges so far.
 __global__ void __launch_bounds__(256)
     halo_exchange_kernel(FieldTable T, int nx, int ny, int pitch, int depth, PhaseArgs LR, PhaseArgs BT,
-                         unsigned int* counters, unsigned int gen) {
+                         unsigned int* counters, unsigned int gen, unsigned int gen_bc, int4 ext) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
   const unsigned int target = gen * gridDim.x;
   if (LR.n > 0) {
@@ -498,6 +501,14 @@ __global__ void __launch_bounds__(256)
     phase_publish(BT, counters + 2, target);
     phase_wait(BT);
     phase_get(T, nx, ny, pitch, depth, BT, edge, gtid, gsize);
+  }
+  // the reflective boundary of the external faces (update_halo_kernel_c.c) in the same launch: its corner cells
+  // mirror halo cells that the exchange has just delivered, hence the barrier
+  if (ext.x | ext.y | ext.z | ext.w) {
+    grid_barrier(counters + 3, gen_bc * gridDim.x);
+    const int ring = 2 * depth * (nx + 1 + 2 * depth) + 2 * depth * (ny + 1);
+    for (int i = gtid; i < ring * T.n; i += gsize)
+      update_halo_item(T.f[i / ring], nx, ny, pitch, depth, ext.x, ext.y, ext.z, ext.w, i % ring);
   }
 }
 
@@ -605,7 +616,7 @@ __global__ void __launch_bounds__(P2P_MAX_RANKS)
 }
 
 // the whole exchange (both phases) through peer memory: one cooperative launch
-static void p2p_exchange(const Grid& g, const HaloArgs& h) {
+static void p2p_exchange(const Grid& g, const HaloArgs& h, const HaloArgs* bc) {
   const int* nb = chunk_neighbours();
   const FieldTable T = [&] {
     // message offsets differ between the phases (edge length); they are recomputed in the kernel from the
@@ -655,7 +666,11 @@ static void p2p_exchange(const Grid& g, const HaloArgs& h) {
   const unsigned int gen = ++PP.gen;
   int nx = g.nx, ny = g.ny, pitch = g.pitch, depth = h.depth;
   FieldTable Tc = T;
-  void* args[] = {&Tc, &nx, &ny, &pitch, &depth, &ph[0], &ph[1], &counters, (void*)&gen};
+  int4 ext = make_int4(0, 0, 0, 0);
+  if (bc) ext = make_int4(bc->ext[0], bc->ext[1], bc->ext[2], bc->ext[3]);
+  if (ext.x | ext.y | ext.z | ext.w) ++PP.gen_bc;
+  unsigned int gen_bc = PP.gen_bc;
+  void* args[] = {&Tc, &nx, &ny, &pitch, &depth, &ph[0], &ph[1], &counters, (void*)&gen, &gen_bc, &ext};
   LaunchScope ls("halo_exchange_p2p");
   CLV_CUDA(cudaLaunchCooperativeKernel((void*)halo_exchange_kernel, dim3((unsigned)ctas), dim3(256), args, 0, stream()));
 }
@@ -702,7 +717,7 @@ void run_exchange(const Grid& g, const HaloArgs& h) {
   const int* nb = chunk_neighbours();
   const int depth = h.depth;
   if (p2p_setup(g)) {
-    p2p_exchange(g, h);
+    p2p_exchange(g, h, nullptr);
     return;
   }
   for (int phase = 0; phase < 2; ++phase) {
@@ -730,6 +745,23 @@ void run_exchange(const Grid& g, const HaloArgs& h) {
       launch_message(true, T, g, depth, face, N.rcv[face]);
     }
   }
+}
+
+// clover_exchange followed by update_halo_kernel with the same field list (update_halo.f90:39-113): one launch when
+// the peer-memory transport is up and the chunk is wide enough for the one-pass reflection.
+void run_exchange_then_halo(const Grid& g, const HaloArgs* ex, const HaloArgs* uh) {
+  if (ex && uh && g.nx >= uh->depth + 1 && g.ny >= uh->depth + 1 && ex->depth == uh->depth && p2p_setup(g)) {
+    bool same = true;
+    for (int f = 0; f < 15; ++f) same = same && (ex->fields[f] == uh->fields[f]) && (!ex->fields[f] || ex->host[f] == uh->host[f]);
+    const int* nb = chunk_neighbours();
+    const bool any_nb = nb[0] != -1 || nb[1] != -1 || nb[2] != -1 || nb[3] != -1;
+    if (same && any_nb) {
+      p2p_exchange(g, *ex, uh);
+      return;
+    }
+  }
+  if (ex) run_exchange(g, *ex);
+  if (uh) run_update_halo(g, *uh);
 }
 
 }  // namespace clv
