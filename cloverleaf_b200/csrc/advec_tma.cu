@@ -432,7 +432,7 @@ void run_advec_cell_tma(const Grid& g, int dir, int sweep, double* vertexdx, dou
   double* d_new = dev_alt(g, density1, CELL);
   double* e_new = dev_alt(g, energy1, CELL);
   const double* vd = dir == 1 ? dev(g, vertexdx, X1D_VERT, IN) : dev(g, vertexdy, Y1D_VERT, IN);
-  double* mf = dir == 1 ? dev(g, mass_flux_x, XFACE, OUT) : dev(g, mass_flux_y, YFACE, OUT);
+  double* mf = dir == 1 ? dev(g, mass_flux_x, XFACE, OUT_FULL) : dev(g, mass_flux_y, YFACE, OUT_FULL);
   const double* in[CA_NARR] = {vol, fx, fy, d_old, e_old};
   CellMaps M;
   static int cx = -1, cy = -1;

@@ -755,9 +755,9 @@ static size_t fuse_timestep(const Op* q, size_t n, size_t i) {
     const double* vol = dev(g, volume, CELL, IN);
     const double* d0 = dev(g, density0, CELL, IN);
     const double* e0 = dev(g, energy0, CELL, IN);
-    double* p = dev(g, pressure, CELL, OUT);
-    double* qv = dev(g, viscosity, CELL, OUT);
-    double* ss = dev(g, soundspeed, CELL, OUT);
+    double* p = dev(g, pressure, CELL, OUT_FULL);
+    double* qv = dev(g, viscosity, CELL, OUT_FULL);
+    double* ss = dev(g, soundspeed, CELL, OUT_FULL);
     const double* xv = dev(g, xvel0, VERTEX, IN);
     const double* yv = dev(g, yvel0, VERTEX, IN);
     const DtParams P{dt.sv[0], dt.sv[1], dt.sv[2], dt.sv[3], dt.sv[4], dt.sv[5]};
@@ -905,8 +905,8 @@ static size_t fuse_correct(const Op* q, size_t n, size_t i) {
   A.yvel1 = dev(g, yvel1, VERTEX, OUT_FULL);
   A.density1 = dev(g, density1, CELL, OUT_FULL);
   A.energy1 = dev(g, energy1, CELL, OUT_FULL);
-  A.vol_flux_x = dev(g, vol_flux_x, XFACE, OUT);
-  A.vol_flux_y = dev(g, vol_flux_y, YFACE, OUT);
+  A.vol_flux_x = dev(g, vol_flux_x, XFACE, OUT_FULL);
+  A.vol_flux_y = dev(g, vol_flux_y, YFACE, OUT_FULL);
   if (tma_enabled()) {
     static int cfg = -1;
     if (cfg < 0) cfg = getenv("CLOVER_B200_LT_CFG") ? atoi(getenv("CLOVER_B200_LT_CFG")) : 1;

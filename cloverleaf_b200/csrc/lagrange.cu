@@ -354,8 +354,8 @@ void launch_copy_range(const Grid& g, const double* src, double* dst, Kind kind)
 void run_ideal_gas(const Grid& g, double* density, double* energy, double* pressure, double* soundspeed) {
   const double* d = dev(g, density, CELL, IN);
   const double* e = dev(g, energy, CELL, IN);
-  double* p = dev(g, pressure, CELL, OUT);
-  double* ss = dev(g, soundspeed, CELL, OUT);
+  double* p = dev(g, pressure, CELL, OUT_FULL);
+  double* ss = dev(g, soundspeed, CELL, OUT_FULL);
   const Range r = make_range(1, g.nx, 1, g.ny);
   LaunchScope ls("ideal_gas");
   ideal_gas_kernel<NR_IDEAL><<<grid_for(r, NR_IDEAL), dim3(BX, BY), 0, stream()>>>(r, g.pitch, d, e, p, ss);
@@ -367,7 +367,7 @@ void run_viscosity(const Grid& g, double* celldx, double* celldy, double* densit
   const double* cdy = dev(g, celldy, Y1D_CELL, IN);
   const double* d0 = dev(g, density0, CELL, IN);
   const double* p = dev(g, pressure, CELL, IN);
-  double* q = dev(g, viscosity, CELL, OUT);
+  double* q = dev(g, viscosity, CELL, OUT_FULL);
   const double* xv = dev(g, xvel0, VERTEX, IN);
   const double* yv = dev(g, yvel0, VERTEX, IN);
   const Range r = make_range(1, g.nx, 1, g.ny);
@@ -507,8 +507,8 @@ void run_flux_calc(const Grid& g, double dt, double* xarea, double* yarea, doubl
   const double* y0 = dev(g, yvel0, VERTEX, IN);
   const double* x1 = dev(g, xvel1, VERTEX, IN);
   const double* y1 = dev(g, yvel1, VERTEX, IN);
-  double* fx = dev(g, vol_flux_x, XFACE, OUT);
-  double* fy = dev(g, vol_flux_y, YFACE, OUT);
+  double* fx = dev(g, vol_flux_x, XFACE, OUT_FULL);
+  double* fy = dev(g, vol_flux_y, YFACE, OUT_FULL);
   const Range r = make_range(1, g.nx + 1, 1, g.ny + 1);
   LaunchScope ls("flux_calc");
   flux_calc_kernel<NR_FLUX><<<grid_for(r, NR_FLUX), dim3(BX, BY), 0, stream()>>>(r, g.pitch, g.nx, g.ny, dt, xa, ya, x0,

@@ -103,6 +103,26 @@ void upload(const Entry& e, const double* host) {
   }
 }
 
+// First sight of an array that the call is about to overwrite on its whole update range (OUT_FULL): only the cells
+// outside that range -- two rows below and above, two columns left and right -- carry information from the host.
+// Update ranges: cell 1..nx x 1..ny, vertex 1..nx+1 x 1..ny+1, x-face 1..nx+1 x 1..ny, y-face 1..nx x 1..ny+1.
+void upload_ring(const Entry& e, const double* host) {
+  const int pitch = pitch_for(e.nx);
+  const int roww = host_row(e.kind, e.nx), rows = host_rows(e.kind, e.ny);
+  const int nj = e.nx + ((e.kind == VERTEX || e.kind == XFACE) ? 1 : 0);
+  const int nk = e.ny + ((e.kind == VERTEX || e.kind == YFACE) ? 1 : 0);
+  const int jmax = roww - 2, kmax = rows - 2;  // last Fortran index of the extent (lower bound -1)
+  const size_t sp = (size_t)roww * sizeof(double), dp = (size_t)pitch * sizeof(double);
+  auto h = [&](int j, int k) { return host + (size_t)(k + 1) * roww + (j + 1); };
+  auto d = [&](int j, int k) { return e.d + idx2(pitch, j, k); };
+  CLV_CUDA(cudaMemcpy2DAsync(d(-1, -1), dp, h(-1, -1), sp, sp, 2, cudaMemcpyHostToDevice, R.stream));
+  CLV_CUDA(cudaMemcpy2DAsync(d(-1, nk + 1), dp, h(-1, nk + 1), sp, sp, kmax - nk, cudaMemcpyHostToDevice, R.stream));
+  CLV_CUDA(cudaMemcpy2DAsync(d(-1, 1), dp, h(-1, 1), sp, 2 * sizeof(double), nk, cudaMemcpyHostToDevice, R.stream));
+  CLV_CUDA(cudaMemcpy2DAsync(d(nj + 1, 1), dp, h(nj + 1, 1), sp, (size_t)(jmax - nj) * sizeof(double), nk,
+                             cudaMemcpyHostToDevice, R.stream));
+  R.h2d += (long long)(sp * (2 + kmax - nk) + (size_t)(2 + jmax - nj) * sizeof(double) * nk);
+}
+
 void download(const Entry& e, double* host) {
   if (is_2d(e.kind)) {
     const int pitch = pitch_for(e.nx);
@@ -277,7 +297,8 @@ double* dev(const Grid& g, const double* host, Kind kind, int access) {
   // Resident mode: the host copy is authoritative only the first time the address is seen.
   // Copy-in/out mode: it is authoritative on every call (outputs too: a kernel writes only its
   // loop range, the rest of the array must survive the round trip).
-  if (fresh || !R.resident) upload(e, host);
+  if (fresh && R.resident && access == OUT_FULL && is_2d(kind)) upload_ring(e, host);
+  else if (fresh || !R.resident) upload(e, host);
   if (!R.resident && (access & (OUT | HALO))) R.pending_out.push_back(host);
   return e.d;
 }
