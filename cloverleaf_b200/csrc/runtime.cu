@@ -626,6 +626,12 @@ void clover_b200_set_fusion_(int* on) {
   R.fuse = (*on != 0);
 }
 
+void clover_b200_set_tma_(int* on) {
+  ensure_init();
+  flush_deferred();
+  R.tma = (*on != 0);
+}
+
 void clover_b200_profile_reset_(void) { R.prof.clear(); }
 
 void clover_b200_profile_get_(int* max, char* names32, double* total_ms, long long* calls, int* n) {

@@ -182,6 +182,9 @@ void clover_b200_set_resident_(int *on);
  * advec_mom x/y velocity pairs, and reset_field / revert become buffer swaps / lazy copies.  Array
  * contents at every host-observable point are bit-identical with fusion on or off. */
 void clover_b200_set_fusion_(int *on);
+/* 1 (default): the fused launches stream their inputs through TMA tile staging (csrc/tma.cuh); 0: the register /
+ * L2-prefetch variants of the same launches (A/B profiling, tests).  Results are bit-identical either way. */
+void clover_b200_set_tma_(int *on);
 /* Forget all device mirrors (the host arrays were modified behind the library's back). */
 void clover_b200_invalidate_(void);
 /* Forget the mirror of ONE host array (call before the host frees / re-uses that address). */

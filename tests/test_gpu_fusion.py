@@ -26,6 +26,11 @@ def _set_fusion(lib, on):
     lib.clover_b200_set_fusion_(ctypes.byref(v))
 
 
+def _set_tma(lib, on):
+    v = ctypes.c_int(1 if on else 0)
+    lib.clover_b200_set_tma_(ctypes.byref(v))
+
+
 def _fields(lib, d):
     out = {}
     for f in FIELDS:
@@ -39,8 +44,10 @@ def _fields(lib, d):
 def fresh(b200):
     b200.clover_b200_invalidate_()
     _set_fusion(b200, True)
+    _set_tma(b200, True)
     yield b200
     _set_fusion(b200, True)
+    _set_tma(b200, True)
     b200.clover_b200_invalidate_()
 
 
@@ -50,17 +57,20 @@ def test_fused_equals_unfused_equals_oracle(fresh, nx, ny, steps):
     deck = _deck(nx, ny)
     o = Driver(deck, ORACLE_PORT, end_step=steps); o.run()
     runs = {}
-    for fuse in (True, False):
+    # fused + TMA tile staging (the production path), fused with the register/L2-prefetch kernels, call by call
+    for mode, (fuse, tma) in dict(tma=(True, True), fused=(True, False), unfused=(False, False)).items():
         fresh.clover_b200_invalidate_()
         _set_fusion(fresh, fuse)
+        _set_tma(fresh, tma)
         d = Driver(deck, cloverleaf_b200.LIB_B200, end_step=steps); d.run()
-        runs[fuse] = (d.dts().copy(), _fields(fresh, d))
+        runs[mode] = (d.dts().copy(), _fields(fresh, d))
         d.close()
-    assert np.array_equal(o.dts(), runs[True][0]) and np.array_equal(o.dts(), runs[False][0])
+    for mode in runs:
+        assert np.array_equal(o.dts(), runs[mode][0]), mode + " dt"
     for f in FIELDS:
         ref = o.field(f)
-        assert np.array_equal(ref, runs[False][1][f]), "unfused " + f
-        assert np.array_equal(ref, runs[True][1][f]), "fused " + f
+        for mode in runs:
+            assert np.array_equal(ref, runs[mode][1][f]), mode + " " + f
 
 
 def test_mid_run_downloads_do_not_disturb(fresh):
