@@ -352,26 +352,32 @@ __global__ void generate_chunk_kernel(States S, int nx, int ny, int pitch, const
 // ------------------------------------------------------------------------------------------------
 // Halo exchange over peer memory (NVLink / NVSwitch), no library call on the data path.
 //
-// Every rank owns one device block  [512 B header | face 0 slot 0 | face 0 slot 1 | face 1 slot 0 | ...]  that its
-// four neighbours can address (cudaIpc* handles, exchanged once with ncclAllGather).  One exchange phase
-// (left/right, then bottom/top -- the reference's order, clover.f90:377-500, which is what propagates the
-// corners) is two launches:
-//   put: packs the strips of all requested fields (message layout of pack_kernel_c.c, per-field offsets of
-//        clover.f90:368-375) STRAIGHT INTO THE NEIGHBOUR's receive slot with ordinary stores through NVLink; the
-//        last CTA of a face publishes the exchange's sequence number in the neighbour's header (release, system
-//        scope);
-//   get: waits (acquire, system scope) until its own header shows that sequence number and unpacks.
-// Two slots per face, used alternately: a neighbour can only start writing exchange n+2 after it has received
-// my exchange n+1, which I sent after unpacking n (stream order), so slot n&1 is free again by then.
+// Every rank owns one device block  [header | 4 face slots x2 | 4 corner slots x2]  that every rank can address
+// (cudaIpc* handles, exchanged once with ncclAllGather).  An exchange is ONE launch and ONE network round trip:
+//   put:     the left/right and bottom/top strips of all requested fields (message layout of pack_kernel_c.c,
+//            per-field offsets of clover.f90:368-375, own rows/columns only) go STRAIGHT INTO THE NEIGHBOUR's receive
+//            slot with ordinary stores through NVLink, and the depth x depth corner blocks go to the four DIAGONAL
+//            neighbours.  (The reference gets the corners by running left/right before bottom/top, clover.f90:377-500:
+//            the bottom/top strips then carry the halo columns just received.  The value that ends up in a corner cell
+//            is the diagonal neighbour's interior cell either way; corner cells next to an external face are
+//            rewritten by the reflective boundary that follows, as in the reference.)
+//   publish: the last CTA to finish writes the exchange's sequence number into every peer's header (st.release.sys);
+//   wait:    until my header shows that number for every face/corner that has a peer (ld.acquire.sys);
+//   get:     unpack;  then a grid barrier and the reflective boundary of the external faces (update_halo_kernel).
+// Two slots per face/corner, used alternately: a peer can only start writing exchange n+2 after it has received my
+// exchange n+1, which I sent after unpacking n (stream order), so slot n&1 is free again by then.
 constexpr int P2P_MAX_RANKS = 64;
 constexpr int AR_OFF = 1024, AR_SLOT = 128;  // all-reduce mailboxes: [parity][sender rank] x {8 values, sequence number}
+constexpr int CORNER_SLOT = 512;  // 15 fields x 2x2 doubles
 constexpr int P2P_HEADER = AR_OFF + 2 * P2P_MAX_RANKS * AR_SLOT;  // flags at face*64, tickets at 256, mailboxes at 1024
 struct PeerInfo {  // what a rank publishes about its block
   cudaIpcMemHandle_t handle;
   unsigned long long off[4];   // byte offset of slot 0 of my face f
   unsigned long long slot[4];  // slot size in bytes
   unsigned long long ok;
-  unsigned long long pad[7];
+  unsigned long long corner_off;  // byte offset of corner slot (corner 0, parity 0); CORNER_SLOT bytes each, [parity][corner]
+  int nb[4];                      // chunk_neighbours (chunk ids, -1 = external)
+  unsigned long long pad[4];
 };
 static_assert(sizeof(PeerInfo) == 192, "PeerInfo is exchanged as raw bytes");
 struct P2P {
@@ -380,91 +386,93 @@ struct P2P {
   unsigned long long off[4] = {}, slot[4] = {};
   unsigned char* peer[4] = {};            // the block of the neighbour across my face f
   unsigned long long peer_off[4] = {}, peer_slot[4] = {};  // layout of the neighbour's face opposite to f
-  unsigned long long seq[4] = {};
+  unsigned long long corner_off = 0;
+  int diag[4] = {-1, -1, -1, -1};         // rank of the diagonal neighbour: 0 bottom-left, 1 bottom-right, 2 top-left, 3 top-right
+  unsigned long long diag_corner_off[4] = {};
   unsigned int gen = 0, gen_bc = 0;  // exchange launches so far / of those, the ones that also did the boundary
   unsigned char* all[P2P_MAX_RANKS] = {};  // every rank's block (mine included)
   unsigned char** d_all = nullptr;         // the same table on the device
   unsigned long long ar_seq = 0;
 } PP;
 
-struct PhaseArgs {
-  int n;                        // faces in this phase that have a neighbour (1 or 2)
-  int face[2];
-  double* buf[2];               // put: the neighbour's slot for this exchange
-  double* mine[2];              // get: my slot
-  unsigned long long* flag_out[2];  // the neighbour's flag for its face opposite to mine
-  unsigned long long* flag_in[2];   // my flag for this face
-  unsigned long long seq[2];
+struct XArgs {
+  int nface;                         // faces that have a neighbour
+  int face[4];
+  double* fbuf[4];                   // the neighbour's slot for this exchange
+  double* fmine[4];                  // my slot
+  int ncorner;                       // corners that have a diagonal neighbour
+  int corner[4];                     // 0 bottom-left, 1 bottom-right, 2 top-left, 3 top-right (as seen from me)
+  double* cbuf[4];
+  double* cmine[4];
+  int nflag;                         // peers to notify / to wait for (faces first, then corners)
+  unsigned long long* flag_out[8];
+  unsigned long long* flag_in[8];
+  unsigned long long seq;
 };
 
+// strip element t of field F on `face` -> field cell (j,k) and message index; only the rank's own rows (left/right)
+// resp. columns (bottom/top) travel, the corners have their own messages
 __device__ __forceinline__ void message_index(const FieldDesc& F, int nx, int ny, int depth, int face, bool unpack,
                                               int t, int& j, int& k, int& index, bool& valid) {
   if (face < 2) {
     const int span = ny + F.y_inc + 2 * depth;
-    valid = t < span * depth;
     const int jj = t % depth + 1, kk = t / depth;
     k = kk - depth + 1;
+    valid = t < span * depth && k >= 1 && k <= ny + F.y_inc;
     index = F.offset * depth * (ny + 5) + (jj - 1) + kk * depth;
     if (face == 0) j = unpack ? 1 - jj : 1 + F.x_inc - 1 + jj;
     else           j = unpack ? nx + F.x_inc + jj : nx + 1 - jj;
   } else {
     const int span = nx + F.x_inc + 2 * depth;
-    valid = t < span * depth;
     const int kk = t / span + 1, jx = t % span;
     j = jx - depth + 1;
+    valid = t < span * depth && j >= 1 && j <= nx + F.x_inc;
     index = F.offset * depth * (nx + 5) + (kk - 1) + jx * depth;
     if (face == 2) k = unpack ? 1 - kk : 1 + F.y_inc - 1 + kk;
     else           k = unpack ? ny + F.y_inc + kk : ny + 1 - kk;
   }
 }
+// corner element t (= (kk-1)*depth + jj-1) of field F: the cell I send towards corner c / the halo cell I fill at c
+__device__ __forceinline__ void corner_index(const FieldDesc& F, int nx, int ny, int depth, int c, bool unpack, int t,
+                                             int& j, int& k) {
+  const int jj = t % depth + 1, kk = t / depth + 1;
+  const bool left = (c & 1) == 0, bottom = (c & 2) == 0;
+  if (unpack) {
+    j = left ? 1 - jj : nx + F.x_inc + jj;
+    k = bottom ? 1 - kk : ny + F.y_inc + kk;
+  } else {
+    j = left ? 1 + F.x_inc - 1 + jj : nx + 1 - jj;
+    k = bottom ? 1 + F.y_inc - 1 + kk : ny + 1 - kk;
+  }
+}
 
-// put (both faces of the phase) -> publish -> wait -> get, executed by a grid that is resident as a whole
-__device__ __forceinline__ void phase_put(const FieldTable& T, int nx, int ny, int pitch, int depth, const PhaseArgs& A,
-                                          int edge, int gtid, int gsize) {
-  const int per_field = edge * depth, per_face = per_field * T.n;
-  for (int i = gtid; i < per_face * A.n; i += gsize) {
-    const int z = i / per_face, r = i - z * per_face, f = r / per_field, t = r - f * per_field;
-    const FieldDesc& F = T.f[f];
-    int j, k, index;
-    bool valid;
-    message_index(F, nx, ny, depth, A.face[z], false, t, j, k, index, valid);
-    if (valid) A.buf[z][index] = F.p[idx2(pitch, j, k)];
-  }
-}
-__device__ __forceinline__ void phase_get(const FieldTable& T, int nx, int ny, int pitch, int depth, const PhaseArgs& A,
-                                          int edge, int gtid, int gsize) {
-  const int per_field = edge * depth, per_face = per_field * T.n;
-  for (int i = gtid; i < per_face * A.n; i += gsize) {
-    const int z = i / per_face, r = i - z * per_face, f = r / per_field, t = r - f * per_field;
-    const FieldDesc& F = T.f[f];
-    int j, k, index;
-    bool valid;
-    message_index(F, nx, ny, depth, A.face[z], true, t, j, k, index, valid);
-    if (valid) F.p[idx2(pitch, j, k)] = __ldcg(A.mine[z] + index);
-  }
-}
-// all CTAs have finished their part: the last one to arrive publishes the sequence numbers to the neighbours
-__device__ __forceinline__ void phase_publish(const PhaseArgs& A, unsigned int* ticket, unsigned int target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    if (atomicAdd(ticket, 1u) + 1 == target) {
-      __threadfence_system();
-      for (int z = 0; z < A.n; ++z)
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.flag_out[z]), "l"(A.seq[z]) : "memory");
+template <bool UNPACK>
+__device__ __forceinline__ void exchange_copy(const FieldTable& T, int nx, int ny, int pitch, int depth, const XArgs& A,
+                                              int gtid, int gsize) {
+  for (int z = 0; z < A.nface; ++z) {
+    const int face = A.face[z];
+    const int per_field = ((face < 2 ? ny : nx) + 1 + 2 * depth) * depth;
+    for (int i = gtid; i < per_field * T.n; i += gsize) {
+      const int f = i / per_field, t = i - f * per_field;
+      const FieldDesc& F = T.f[f];
+      int j, k, index;
+      bool valid;
+      message_index(F, nx, ny, depth, face, UNPACK, t, j, k, index, valid);
+      if (valid) {
+        if (UNPACK) F.p[idx2(pitch, j, k)] = __ldcg(A.fmine[z] + index);
+        else        A.fbuf[z][index] = F.p[idx2(pitch, j, k)];
+      }
     }
   }
-}
-__device__ __forceinline__ void phase_wait(const PhaseArgs& A) {
-  if (threadIdx.x == 0) {
-    for (int z = 0; z < A.n; ++z) {
-      unsigned long long v;
-      do {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(A.flag_in[z]) : "memory");
-      } while (v < A.seq[z]);
-    }
+  const int per_corner = depth * depth;
+  for (int i = gtid; i < A.ncorner * T.n * per_corner; i += gsize) {
+    const int z = i / (T.n * per_corner), r = i - z * (T.n * per_corner), f = r / per_corner, t = r - f * per_corner;
+    const FieldDesc& F = T.f[f];
+    int j, k;
+    corner_index(F, nx, ny, depth, A.corner[z], UNPACK, t, j, k);
+    if (UNPACK) F.p[idx2(pitch, j, k)] = __ldcg(A.cmine[z] + f * per_corner + t);
+    else        A.cbuf[z][f * per_corner + t] = F.p[idx2(pitch, j, k)];
   }
-  __syncthreads();
 }
 // grid-wide barrier (the grid is launched cooperatively: all CTAs are resident)
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
@@ -479,28 +487,32 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
-// One launch per exchange: left/right phase, then bottom/top phase over the freshly received left/right halos.
-// `counters` are three monotonically increasing tickets in my header; `gen` = number of exchanges so far.
+// `counters`: monotonically increasing tickets in my header; `gen` = number of exchanges so far (= the sequence
+// number every rank uses for this exchange), `gen_bc` = the ones among them that also did the boundary.
 __global__ void __launch_bounds__(256)
-    halo_exchange_kernel(FieldTable T, int nx, int ny, int pitch, int depth, PhaseArgs LR, PhaseArgs BT,
-                         unsigned int* counters, unsigned int gen, unsigned int gen_bc, int4 ext) {
+    halo_exchange_kernel(FieldTable T, int nx, int ny, int pitch, int depth, XArgs A, unsigned int* counters,
+                         unsigned int gen, unsigned int gen_bc, int4 ext) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
-  const unsigned int target = gen * gridDim.x;
-  if (LR.n > 0) {
-    const int edge = ny + 1 + 2 * depth;
-    phase_put(T, nx, ny, pitch, depth, LR, edge, gtid, gsize);
-    phase_publish(LR, counters + 0, target);
-    phase_wait(LR);
-    phase_get(T, nx, ny, pitch, depth, LR, edge, gtid, gsize);
-  }
-  if (BT.n > 0) {
-    // the bottom/top strips include the corner cells the left/right phase has just delivered
-    if (LR.n > 0) grid_barrier(counters + 1, target);
-    const int edge = nx + 1 + 2 * depth;
-    phase_put(T, nx, ny, pitch, depth, BT, edge, gtid, gsize);
-    phase_publish(BT, counters + 2, target);
-    phase_wait(BT);
-    phase_get(T, nx, ny, pitch, depth, BT, edge, gtid, gsize);
+  if (A.nflag > 0) {
+    exchange_copy<false>(T, nx, ny, pitch, depth, A, gtid, gsize);
+    // publish: the last CTA to arrive tells every peer
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      if (atomicAdd(counters + 0, 1u) + 1 == gen * gridDim.x) {
+        __threadfence_system();
+        for (int z = 0; z < A.nflag; ++z)
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.flag_out[z]), "l"(A.seq) : "memory");
+      }
+      for (int z = 0; z < A.nflag; ++z) {
+        unsigned long long v;
+        do {
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(A.flag_in[z]) : "memory");
+        } while (v < A.seq);
+      }
+    }
+    __syncthreads();
+    exchange_copy<true>(T, nx, ny, pitch, depth, A, gtid, gsize);
   }
   // the reflective boundary of the external faces (update_halo_kernel_c.c) in the same launch: its corner cells
   // mirror halo cells that the exchange has just delivered, hence the barrier
@@ -524,13 +536,16 @@ static bool p2p_setup(const Grid& g) {
     PP.off[f] = bytes;
     bytes += 2 * PP.slot[f];
   }
+  PP.corner_off = bytes;
+  bytes += 2 * 4 * CORNER_SLOT;
   CLV_CUDA(cudaMalloc(&PP.mine, bytes));
   CLV_CUDA(cudaMemset(PP.mine, 0, bytes));
   PeerInfo me;
   memset(&me, 0, sizeof(me));
   me.ok = (cudaIpcGetMemHandle(&me.handle, PP.mine) == cudaSuccess) ? 1 : 0;
   (void)cudaGetLastError();
-  for (int f = 0; f < 4; ++f) { me.off[f] = PP.off[f]; me.slot[f] = PP.slot[f]; }
+  for (int f = 0; f < 4; ++f) { me.off[f] = PP.off[f]; me.slot[f] = PP.slot[f]; me.nb[f] = nb[f]; }
+  me.corner_off = PP.corner_off;
   // publish / collect
   unsigned char* d_all = nullptr;
   CLV_CUDA(cudaMalloc(&d_all, (size_t)(N.nranks + 1) * sizeof(PeerInfo)));
@@ -557,6 +572,16 @@ static bool p2p_setup(const Grid& g) {
     PP.peer_off[f] = q.off[f ^ 1];
     PP.peer_slot[f] = q.slot[f ^ 1];
     if (PP.peer_slot[f] != PP.slot[f]) ok = 0.0;  // both sides of a face see the same edge length
+  }
+  // diagonal neighbours: the bottom/top neighbour of my left/right neighbour (clover.f90:180-188 numbering)
+  for (int c = 0; c < 4 && ok > 0; ++c) {
+    const int fx = (c & 1) ? 1 : 0, fy = (c & 2) ? 3 : 2;  // face towards the corner: left/right, bottom/top
+    PP.diag[c] = -1;
+    if (nb[fx] == -1 || nb[fy] == -1) continue;
+    const int via_x = all[nb[fx] - 1].nb[fy], via_y = all[nb[fy] - 1].nb[fx];
+    if (via_x == -1 || via_x != via_y) { ok = 0.0; break; }  // not a rectangular decomposition
+    PP.diag[c] = via_x - 1;
+    PP.diag_corner_off[c] = all[via_x - 1].corner_off;
   }
   if (ok > 0) {
     CLV_CUDA(cudaMalloc(&PP.d_all, sizeof(PP.all)));
@@ -635,23 +660,33 @@ static void p2p_exchange(const Grid& g, const HaloArgs& h, const HaloArgs* bc) {
     return t;
   }();
   if (T.n == 0) return;
-  PhaseArgs ph[2];
-  for (int phase = 0; phase < 2; ++phase) {
-    PhaseArgs& A = ph[phase];
-    A.n = 0;
-    for (int face = 2 * phase; face <= 2 * phase + 1; ++face) {
-      if (nb[face] == -1) continue;
-      const unsigned long long seq = ++PP.seq[face];
-      const int i = A.n++;
-      A.face[i] = face;
-      A.seq[i] = seq;
-      A.buf[i] = (double*)(PP.peer[face] + PP.peer_off[face] + (seq & 1) * PP.peer_slot[face]);
-      A.mine[i] = (double*)(PP.mine + PP.off[face] + (seq & 1) * PP.slot[face]);
-      A.flag_out[i] = (unsigned long long*)(PP.peer[face] + (face ^ 1) * 64);
-      A.flag_in[i] = (unsigned long long*)(PP.mine + face * 64);
-    }
+  const unsigned int gen = ++PP.gen;
+  XArgs A;
+  A.nface = A.ncorner = A.nflag = 0;
+  A.seq = gen;
+  const size_t par = gen & 1;
+  for (int face = 0; face < 4; ++face) {
+    if (nb[face] == -1) continue;
+    const int i = A.nface++;
+    A.face[i] = face;
+    A.fbuf[i] = (double*)(PP.peer[face] + PP.peer_off[face] + par * PP.peer_slot[face]);
+    A.fmine[i] = (double*)(PP.mine + PP.off[face] + par * PP.slot[face]);
+    A.flag_out[A.nflag] = (unsigned long long*)(PP.peer[face] + (face ^ 1) * 64);
+    A.flag_in[A.nflag] = (unsigned long long*)(PP.mine + face * 64);
+    A.nflag++;
   }
-  if (ph[0].n == 0 && ph[1].n == 0) return;
+  for (int c = 0; c < 4; ++c) {
+    if (PP.diag[c] < 0) continue;
+    const int i = A.ncorner++;
+    A.corner[i] = c;
+    unsigned char* peer = PP.all[PP.diag[c]];
+    // I fill the peer's opposite corner (3 - c) and the peer fills my corner c
+    A.cbuf[i] = (double*)(peer + PP.diag_corner_off[c] + (par * 4 + (3 - c)) * CORNER_SLOT);
+    A.cmine[i] = (double*)(PP.mine + PP.corner_off + (par * 4 + c) * CORNER_SLOT);
+    A.flag_out[A.nflag] = (unsigned long long*)(peer + 512 + (3 - c) * 64);
+    A.flag_in[A.nflag] = (unsigned long long*)(PP.mine + 512 + c * 64);
+    A.nflag++;
+  }
   static int ctas = 0;
   if (!ctas) {
     int per_sm = 0;
@@ -663,14 +698,13 @@ static void p2p_exchange(const Grid& g, const HaloArgs& h, const HaloArgs* bc) {
     ctas = sms;  // one CTA per SM is enough for <= 0.5 MB of strips and keeps the grid barrier cheap
   }
   unsigned int* counters = (unsigned int*)(PP.mine + 256);
-  const unsigned int gen = ++PP.gen;
   int nx = g.nx, ny = g.ny, pitch = g.pitch, depth = h.depth;
   FieldTable Tc = T;
   int4 ext = make_int4(0, 0, 0, 0);
   if (bc) ext = make_int4(bc->ext[0], bc->ext[1], bc->ext[2], bc->ext[3]);
   if (ext.x | ext.y | ext.z | ext.w) ++PP.gen_bc;
   unsigned int gen_bc = PP.gen_bc;
-  void* args[] = {&Tc, &nx, &ny, &pitch, &depth, &ph[0], &ph[1], &counters, (void*)&gen, &gen_bc, &ext};
+  void* args[] = {&Tc, &nx, &ny, &pitch, &depth, &A, &counters, (void*)&gen, &gen_bc, &ext};
   LaunchScope ls("halo_exchange_p2p");
   CLV_CUDA(cudaLaunchCooperativeKernel((void*)halo_exchange_kernel, dim3((unsigned)ctas), dim3(256), args, 0, stream()));
 }
