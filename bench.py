@@ -292,9 +292,16 @@ def _main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    def halo_counters():
+        a, b = cll(0), cll(0)
+        lib.clover_b200_halo_bytes_(ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
     l0 = launches()
+    hb0, hx0 = halo_counters()
     done, ms, wall = timed_steps(d, args.steps)
     l1 = launches()
+    hb1, hx1 = halo_counters()
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(ms)
     cells = nx * ny
@@ -410,6 +417,10 @@ def _main():
                        "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (25 * 8 * chunk_cells / 1e9),
                        "timing": "CUDA events on the library stream, max over ranks; host wall %.3f s" % wall},
             "clocks": clocks, "e2e": e2e, "gpu_launches": l1 - l0,
+            # rank 0's halo traffic (bytes it wrote into its neighbours' memory) against NVLink 5 (900 GB/s per direction)
+            "halo": {"bytes_per_step": (hb1 - hb0) / done, "exchanges_per_step": (hx1 - hx0) / done,
+                     "gbs_over_step": (hb1 - hb0) / (ms * 1e-3) / 1e9,
+                     "frac_of_nvlink_900gbs": (hb1 - hb0) / (ms * 1e-3) / 900e9},
             "roofline": roofline,
             "step_roofline": {"bound": "hbm", "alg_bytes_per_cell_step": ALG_BYTES_PER_CELL_STEP,
                               "achieved": round(step_gbs, 1), "peak": peak, "unit": "GB/s",

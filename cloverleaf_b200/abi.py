@@ -86,7 +86,7 @@ EXTENSION_SYMBOLS = [
     "clover_b200_device_synchronize_", "clover_b200_register_chunk_", "clover_b200_comm_get_unique_id_",
     "clover_b200_comm_init_", "clover_b200_exchange_", "clover_b200_min_", "clover_b200_sum_",
     "clover_b200_launch_count_", "clover_b200_profile_", "clover_b200_profile_get_",
-    "clover_b200_profile_reset_", "clover_b200_copy_bytes_", "clover_b200_event_record_",
+    "clover_b200_profile_reset_", "clover_b200_copy_bytes_", "clover_b200_halo_bytes_", "clover_b200_event_record_",
     "clover_b200_event_elapsed_ms_", "clover_b200_pin_", "clover_b200_unpin_", "clover_b200_selftest_math_",
     "clover_b200_set_fusion_",
     "clover_b200_set_tma_",

@@ -792,11 +792,16 @@ static size_t fuse_timestep(const Op* q, size_t n, size_t i) {
                                                                xv, yv, part, ticket(), host_scalars());
     }
   }
-  {
+  if (ex2 || uh2) {
+    // Nothing reads the viscosity halo before accelerate: its exchange + reflective boundary go to the side stream
+    // and overlap the dt reduction, the host's dt read and the PdV predictor (which joins, fuse_predict below).
     HaloArgs hx, hu;
     if (ex2) hx = halo_args(*ex2, -1);
     if (uh2) hu = halo_args(*uh2, -1);
+    const bool side = overlap_enabled();
+    if (side) side_begin();
     run_exchange_then_halo(g, ex2 ? &hx : nullptr, uh2 ? &hu : nullptr);
+    if (side) side_end();
   }
   return k - i;
 }
@@ -864,6 +869,7 @@ static size_t fuse_predict(const Op* q, size_t n, size_t i) {
                                                                          qv, ss, x0, y0);
     }
   }
+  join_side();  // the viscosity exchange of the timestep pattern, if it is still in flight
   {
     HaloArgs hx, hu;
     if (ex) hx = halo_args(*ex, -1);

@@ -393,6 +393,8 @@ struct P2P {
   unsigned char* all[P2P_MAX_RANKS] = {};  // every rank's block (mine included)
   unsigned char** d_all = nullptr;         // the same table on the device
   unsigned long long ar_seq = 0;
+  long long bytes_sent = 0;                       // through peer memory
+  long long nccl_bytes = 0, nccl_exchanges = 0;  // through the ncclSend/ncclRecv transport
 } PP;
 
 struct XArgs {
@@ -660,6 +662,9 @@ static void p2p_exchange(const Grid& g, const HaloArgs& h, const HaloArgs* bc) {
     return t;
   }();
   if (T.n == 0) return;
+  for (int f = 0; f < 4; ++f)
+    if ((unsigned long long)15 * 2 * ((f < 2 ? g.ny : g.nx) + 5) * sizeof(double) != PP.slot[f])
+      fatal("exchange: chunk %d x %d differs from the one the peer-memory slots were sized for", g.nx, g.ny);
   const unsigned int gen = ++PP.gen;
   XArgs A;
   A.nface = A.ncorner = A.nflag = 0;
@@ -686,6 +691,12 @@ static void p2p_exchange(const Grid& g, const HaloArgs& h, const HaloArgs* bc) {
     A.flag_out[A.nflag] = (unsigned long long*)(peer + 512 + (3 - c) * 64);
     A.flag_in[A.nflag] = (unsigned long long*)(PP.mine + 512 + c * 64);
     A.nflag++;
+  }
+  for (int f = 0; f < 15; ++f) {
+    if (!h.fields[f]) continue;
+    for (int i = 0; i < A.nface; ++i)
+      PP.bytes_sent += (long long)h.depth * ((A.face[i] < 2 ? g.ny + kFieldGeom[f].y_inc : g.nx + kFieldGeom[f].x_inc)) * 8;
+    PP.bytes_sent += (long long)A.ncorner * h.depth * h.depth * 8;
   }
   static int ctas = 0;
   if (!ctas) {
@@ -754,6 +765,7 @@ void run_exchange(const Grid& g, const HaloArgs& h) {
     p2p_exchange(g, h, nullptr);
     return;
   }
+  PP.nccl_exchanges++;
   for (int phase = 0; phase < 2; ++phase) {
     const int fa = phase * 2, fb = fa + 1;
     if (nb[fa] == -1 && nb[fb] == -1) continue;
@@ -771,6 +783,7 @@ void run_exchange(const Grid& g, const HaloArgs& h) {
       if (nb[face] == -1) continue;
       const int peer = nb[face] - 1;  // rank = chunk - 1 (clover.f90:892)
       CLV_NCCL(N.Send(N.snd[face], total, ncclDouble, peer, N.comm, stream()));
+      PP.nccl_bytes += (long long)(total * sizeof(double));
       CLV_NCCL(N.Recv(N.rcv[face], total, ncclDouble, peer, N.comm, stream()));
     }
     CLV_NCCL(N.GroupEnd());
@@ -935,6 +948,11 @@ static void allreduce_host(double* values, int n, ncclRedOp_t op) {
   CLV_NCCL(N.AllReduce(N.d_scal, N.d_scal, (size_t)n, ncclDouble, op, N.comm, stream()));
   CLV_CUDA(cudaMemcpyAsync(values, N.d_scal, n * sizeof(double), cudaMemcpyDeviceToHost, stream()));
   CLV_CUDA(cudaStreamSynchronize(stream()));
+}
+void clover_b200_halo_bytes_(long long* bytes, long long* exchanges) {
+  flush_deferred();
+  *bytes = PP.bytes_sent + PP.nccl_bytes;
+  *exchanges = (long long)PP.gen + PP.nccl_exchanges;
 }
 void clover_b200_min_(double* value) { allreduce_host(value, 1, ncclMin); }
 void clover_b200_sum_(double* values, int* n) { allreduce_host(values, *n, ncclSum); }

@@ -66,6 +66,11 @@ struct Runtime {
   bool draining = false;
   bool fuse = true;
   bool tma = true;
+  bool overlap = true;
+  cudaStream_t side = nullptr;   // second stream: a halo exchange that nothing waits for yet (see side_begin)
+  cudaStream_t cur = nullptr;    // non-null while work is being issued to the side stream
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool side_pending = false;
   int sms = 148;
   int lazy_pending = 0;   // number of entries with lazy_src set
   std::map<std::string, Prof> prof;
@@ -169,12 +174,34 @@ void ensure_init() {
   clover_b200_init_(&dev_id);
 }
 
-cudaStream_t stream() { return R.stream; }
+cudaStream_t stream() { return R.cur ? R.cur : R.stream; }
+
+// Overlap of a halo exchange with the work that does not depend on it (fuse.cu: the viscosity exchange runs next
+// to the dt reduction, the host's dt read and the PdV predictor).  side_begin(): what is issued from now on goes to
+// the side stream, ordered after everything already on the main stream; side_end(): back to the main stream;
+// join_side(): the main stream waits for the side work -- called before anything that could touch its data.
+bool overlap_enabled() { return R.overlap && !R.profiling && R.resident; }
+void side_begin() {
+  CLV_CUDA(cudaEventRecord(R.ev_fork, R.stream));
+  CLV_CUDA(cudaStreamWaitEvent(R.side, R.ev_fork, 0));
+  R.cur = R.side;
+}
+void side_end() {
+  R.cur = nullptr;
+  CLV_CUDA(cudaEventRecord(R.ev_join, R.side));
+  R.side_pending = true;
+}
+void join_side() {
+  if (!R.side_pending) return;
+  CLV_CUDA(cudaStreamWaitEvent(R.stream, R.ev_join, 0));
+  R.side_pending = false;
+}
 
 bool is_resident() { return R.resident; }
 
 Grid grid_of(const int* xmin, const int* xmax, const int* ymin, const int* ymax) {
   flush_deferred();
+  join_side();
   return grid_of_noflush(xmin, xmax, ymin, ymax);
 }
 
@@ -198,8 +225,11 @@ void flush_deferred() {
   std::vector<Op> q;
   q.swap(R.queue);
   for (size_t i = 0; i < q.size();) {
+    // the PdV predictor pattern (fuse.cu) joins the side stream itself, after its compute launch
+    if (q[i].kind != OP_PDV_PREDICT) join_side();
     size_t used = R.fuse ? fuse_at(q.data(), q.size(), i) : 0;
     if (used == 0) {
+      join_side();
       q[i].run();
       used = 1;
     }
@@ -476,6 +506,10 @@ void clover_b200_init_(int* device) {
   if (p.major != 10)
     fatal("device %d is sm_%d%d; this library is built for sm_100a (B200) only", R.device, p.major, p.minor);
   CLV_CUDA(cudaStreamCreateWithFlags(&R.stream, cudaStreamNonBlocking));
+  CLV_CUDA(cudaStreamCreateWithFlags(&R.side, cudaStreamNonBlocking));
+  CLV_CUDA(cudaEventCreateWithFlags(&R.ev_fork, cudaEventDisableTiming));
+  CLV_CUDA(cudaEventCreateWithFlags(&R.ev_join, cudaEventDisableTiming));
+  if (const char* s = getenv("CLOVER_B200_OVERLAP")) R.overlap = (atoi(s) != 0);
   CLV_CUDA(cudaHostAlloc(&R.h_scalars, 64 * sizeof(double), cudaHostAllocMapped));
   CLV_CUDA(cudaMalloc(&R.d_ticket, 16 * sizeof(unsigned int)));
   CLV_CUDA(cudaMemset(R.d_ticket, 0, 16 * sizeof(unsigned int)));
@@ -503,6 +537,10 @@ void clover_b200_finalize_(void) {
   CLV_CUDA(cudaEventDestroy(R.ev0));
   CLV_CUDA(cudaEventDestroy(R.ev1));
   CLV_CUDA(cudaStreamDestroy(R.stream));
+  CLV_CUDA(cudaStreamDestroy(R.side));
+  CLV_CUDA(cudaEventDestroy(R.ev_fork));
+  CLV_CUDA(cudaEventDestroy(R.ev_join));
+  R.side_pending = false;
   R.ready = false;
   C = Chunk();
 }
@@ -510,6 +548,7 @@ void clover_b200_finalize_(void) {
 void clover_b200_set_resident_(int* on) {
   ensure_init();
   flush_deferred();
+  join_side();
   materialize_all();
   CLV_CUDA(cudaStreamSynchronize(R.stream));
   R.resident = (*on != 0);
@@ -518,6 +557,7 @@ void clover_b200_set_resident_(int* on) {
 void clover_b200_invalidate_(void) {
   if (!R.ready) return;
   flush_deferred();
+  join_side();
   CLV_CUDA(cudaStreamSynchronize(R.stream));
   for (auto& kv : R.arrays) {
     CLV_CUDA(cudaFree(kv.second.d));
@@ -534,6 +574,7 @@ void clover_b200_invalidate_(void) {
 void clover_b200_forget_(double* host) {
   if (!R.ready) return;
   flush_deferred();
+  join_side();
   auto it = R.arrays.find(host);
   if (it != R.arrays.end()) {
     materialize_dependents(host);
@@ -555,6 +596,7 @@ void clover_b200_forget_(double* host) {
 void clover_b200_upload_(double* host) {
   ensure_init();
   flush_deferred();
+  join_side();
   auto it = R.arrays.find(host);
   if (it == R.arrays.end()) return;  // never seen: the first use uploads it anyway
   materialize_dependents(host);
@@ -565,6 +607,7 @@ void clover_b200_upload_(double* host) {
 void clover_b200_download_(double* host) {
   ensure_init();
   flush_deferred();
+  join_side();
   auto it = R.arrays.find(host);
   if (it == R.arrays.end()) fatal("download of an array the library has never seen");
   materialize(it->second);
@@ -575,6 +618,7 @@ void clover_b200_download_(double* host) {
 void clover_b200_sync_to_host_(int* fields) {
   ensure_init();
   flush_deferred();
+  join_side();
   if (!C.set) fatal("sync_to_host before register_chunk");
   for (int f = 0; f < 15; ++f) {
     if (fields && fields[f] != 1) continue;
@@ -590,6 +634,7 @@ void clover_b200_sync_to_host_(int* fields) {
 void clover_b200_device_synchronize_(void) {
   ensure_init();
   flush_deferred();
+  join_side();
   CLV_CUDA(cudaStreamSynchronize(R.stream));
 }
 
@@ -669,6 +714,7 @@ extern "C" {
 void clover_b200_event_record_(int* slot) {
   clv::ensure_init();
   clv::flush_deferred();
+  clv::join_side();
   if (*slot < 0 || *slot >= 8) clv::fatal("event slot %d", *slot);
   if (!g_events[*slot]) CLV_CUDA(cudaEventCreate(&g_events[*slot]));
   CLV_CUDA(cudaEventRecord(g_events[*slot], clv::stream()));

@@ -235,6 +235,9 @@ void clover_b200_profile_get_(int *max, char *names32, double *total_ms, long lo
 void clover_b200_profile_reset_(void);
 /* Bytes copied host->device and device->host so far (all modes). */
 void clover_b200_copy_bytes_(long long *h2d, long long *d2h);
+/* Bytes this rank has written into its neighbours' memory (halo strips + corner blocks) and the number of
+ * exchanges so far; bench.py reports the halo traffic against NVLink bandwidth from these. */
+void clover_b200_halo_bytes_(long long *bytes, long long *exchanges);
 
 /* Self-test of the library's branch-free fp64 div / rcp / sqrt against the compiler's IEEE operators
  * on *n pseudo-random + adversarial operand pairs: *mismatches must come back 0; *flagged counts
