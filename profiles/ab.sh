@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: scratch/ab.sh ENVVAR v1 v2 ... ; prints ms/step and per-kernel ms for each value
+# usage: profiles/ab.sh ENVVAR v1 v2 ... ; prints ms/step and per-kernel ms for each value
 var=$1; shift
 for v in "$@"; do
   env $var=$v timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > /tmp/ab.json 2>/tmp/ab.err || { echo "$var=$v FAILED"; tail -3 /tmp/ab.err; continue; }
