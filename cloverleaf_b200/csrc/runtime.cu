@@ -526,6 +526,7 @@ void clover_b200_comm_finalize_internal();
 void clover_b200_finalize_(void) {
   if (!R.ready) return;
   flush_deferred();
+  join_side();
   CLV_CUDA(cudaStreamSynchronize(R.stream));
   clover_b200_comm_finalize_internal();
   clover_b200_invalidate_();
