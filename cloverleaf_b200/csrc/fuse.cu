@@ -111,7 +111,13 @@ __global__ void __launch_bounds__(BX* BY)
 
 // ---- T with TMA tile staging (tma.cuh): persistent CTAs of 32x8 threads, one cell per thread, the seven input
 // fields of a 32x8 tile arrive as 36x10 boxes with corner (j0-2, k0-1).  Same arithmetic as timestep_kernel.
-constexpr int TT_W = BX, TT_H = BY, TT_BW = TT_W + 4, TT_BH = TT_H + 2, TT_NARR = 7, TT_STAGES = 4;
+constexpr int TT_W = BX, TT_H = BY, TT_BW = TT_W + 4, TT_BH = TT_H + 2, TT_NARR = 7;
+#ifndef TT_STAGES
+#define TT_STAGES 4
+#endif
+#ifndef TT_CPS
+#define TT_CPS 2
+#endif
 enum { TA_D0 = 0, TA_E0, TA_U0, TA_V0, TA_VOL, TA_XA, TA_YA };
 using TimestepRing = TileRing<TT_NARR, TT_BW, TT_BH, TT_STAGES>;
 constexpr int TT_SMEM = TimestepRing::BYTES + 128;
@@ -120,7 +126,7 @@ struct TimestepMaps {
 };
 
 template <bool WRITE_SS>
-__global__ void __launch_bounds__(BX* BY, 2)
+__global__ void __launch_bounds__(BX* BY, TT_CPS)
     timestep_tma_kernel(const __grid_constant__ TimestepMaps M, DtParams P, const double* __restrict__ celldx,
                         const double* __restrict__ celldy, const double* __restrict__ density0,
                         const double* __restrict__ energy0, double* __restrict__ pressure,
@@ -778,7 +784,7 @@ static size_t fuse_timestep(const Op* q, size_t n, size_t i) {
       for (int a = 0; a < TT_NARR; ++a) M.m[a] = *tensor_map_for(g, in[a], TT_BW, TT_BH);
       const int ntx = (g.nx + TT_W - 1) / TT_W, nty = (g.ny + TT_H - 1) / TT_H;
       const int ntiles = ntx * nty;
-      const int cap = sm_count() * 2;
+      const int cap = sm_count() * TT_CPS;
       const int ctas = ntiles < cap ? ntiles : cap;
       double* part = partials((size_t)ctas);
       LaunchScope ls("timestep_tma");

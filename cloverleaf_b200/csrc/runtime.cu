@@ -451,6 +451,13 @@ void drop_tensor_maps() {
 }
 }  // namespace
 
+// L2 fetch granularity of the TMA loads (0 none, 1 64 B, 2 128 B, 3 256 B); $CLOVER_B200_L2PROMO overrides for A/B runs
+static int l2_promotion() {
+  static int v = -1;
+  if (v < 0) v = getenv("CLOVER_B200_L2PROMO") ? atoi(getenv("CLOVER_B200_L2PROMO")) : 3;
+  return v;
+}
+
 const CUtensorMap* tensor_map_for(const Grid& g, const double* dev_ptr, int box_w, int box_h) {
   const MapKey key{dev_ptr, g.pitch, g.ny + 6, box_w, box_h};
   auto it = g_maps.find(key);
@@ -470,7 +477,7 @@ const CUtensorMap* tensor_map_for(const Grid& g, const double* dev_ptr, int box_
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)dev_ptr, dims, strides, box, estr,
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                    (CUtensorMapL2promotion)l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     fatal("cuTensorMapEncodeTiled failed (%d) for pitch %d rows %d box %dx%d", (int)r, g.pitch, g.ny + 6, box_w, box_h);
   g_maps[key] = m;
