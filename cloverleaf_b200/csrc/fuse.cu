@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(BX* BY, TT_CPS)
                         const double* __restrict__ celldy, const double* __restrict__ density0,
                         const double* __restrict__ energy0, double* __restrict__ pressure,
                         double* __restrict__ viscosity, double* __restrict__ soundspeed, double* __restrict__ partials,
-                        unsigned int* ticket, double* __restrict__ out, int nx, int ny, int pitch, int ntx, int ntiles) {
+                        unsigned int* ticket, double* __restrict__ out, int nx, int ny, int pitch, int ntx, int ntiles,
+                        const int2* __restrict__ order) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = align128(smem_raw);
   TimestepRing ring;
@@ -140,25 +141,30 @@ __global__ void __launch_bounds__(BX* BY, TT_CPS)
   const bool leader = (lx == 0 && ly == 0);
   const int G = gridDim.x;
   double m[1] = {P.g_big};
-  auto issue_tile = [&](int stage, int t) {
-    const int j0 = 1 + (t % ntx) * TT_W, k0 = 1 + (t / ntx) * TT_H;
+  auto issue_tile = [&](int stage, int2 xy) {
+    const int j0 = 1 + xy.x * TT_W, k0 = 1 + xy.y * TT_H;
     ring.issue(M.m, stage, j0 - 2 + XOFF, k0 - 1 + 1);
   };
   if (leader) {
 #pragma unroll
     for (int s = 0; s < TT_STAGES - 1; ++s) {
       const int t = (int)blockIdx.x + s * G;
-      if (t < ntiles) issue_tile(s, t);
+      if (t < ntiles) issue_tile(s, __ldg(order + t));
     }
   }
+  // tile coordinates: host-built order table (tile_order, tma.cuh), fetched one iteration before they are needed
+  int2 cur = __ldg(order + blockIdx.x), nxt = cur, iss = make_int2(0, 0), iss_nxt = iss;
+  if ((int)blockIdx.x + (TT_STAGES - 1) * G < ntiles) iss = __ldg(order + blockIdx.x + (TT_STAGES - 1) * G);
   int it = 0;
-  for (int t = blockIdx.x; t < ntiles; t += G, ++it) {
+  for (int t = blockIdx.x; t < ntiles; t += G, ++it, cur = nxt, iss = iss_nxt) {
     const int stage = it % TT_STAGES;
     if (leader) {
       const int tn = t + (TT_STAGES - 1) * G;
-      if (tn < ntiles) issue_tile((stage + TT_STAGES - 1) % TT_STAGES, tn);
+      if (tn < ntiles) issue_tile((stage + TT_STAGES - 1) % TT_STAGES, iss);
     }
-    const int j = 1 + (t % ntx) * TT_W + lx, k = 1 + (t / ntx) * TT_H + ly;
+    nxt = (t + G < ntiles) ? __ldg(order + t + G) : cur;
+    iss_nxt = (t + TT_STAGES * G < ntiles) ? __ldg(order + t + TT_STAGES * G) : iss;
+    const int j = 1 + cur.x * TT_W + lx, k = 1 + cur.y * TT_H + ly;
     const bool active = j <= nx && k <= ny;
     const int jc = j <= nx ? j : nx, kc = k <= ny ? k : ny;  // 1-D geometry of the threads beyond the chunk
     const double dsx = celldx[jc + 1], dsy = celldy[kc + 1], dsx1 = celldx[jc + 2], dsy1 = celldy[kc + 2];
@@ -277,7 +283,8 @@ struct PredictMaps {
 template <bool WRITE_SS>
 __global__ void __launch_bounds__(BX* BY, PT_CPS)
     pdv_predict_eos_tma_kernel(const __grid_constant__ PredictMaps M, double dt, double* __restrict__ pressure,
-                               double* __restrict__ soundspeed, int nx, int ny, int pitch, int ntx, int ntiles) {
+                               double* __restrict__ soundspeed, int nx, int ny, int pitch, int ntx, int ntiles,
+                        const int2* __restrict__ order) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = align128(smem_raw);
   PredictRing ring;
@@ -285,25 +292,30 @@ __global__ void __launch_bounds__(BX* BY, PT_CPS)
   const int lx = threadIdx.x, ly = threadIdx.y;
   const bool leader = (lx == 0 && ly == 0);
   const int G = gridDim.x;
-  auto issue_tile = [&](int stage, int t) {
-    const int j0 = 1 + (t % ntx) * PT_W, k0 = 1 + (t / ntx) * PT_H;
+  auto issue_tile = [&](int stage, int2 xy) {
+    const int j0 = 1 + xy.x * PT_W, k0 = 1 + xy.y * PT_H;
     ring.issue(M.m, stage, j0 + XOFF, k0 + 1);
   };
   if (leader) {
 #pragma unroll
     for (int s = 0; s < PT_STAGES - 1; ++s) {
       const int t = (int)blockIdx.x + s * G;
-      if (t < ntiles) issue_tile(s, t);
+      if (t < ntiles) issue_tile(s, __ldg(order + t));
     }
   }
+  // tile coordinates: host-built order table (tile_order, tma.cuh), fetched one iteration before they are needed
+  int2 cur = __ldg(order + blockIdx.x), nxt = cur, iss = make_int2(0, 0), iss_nxt = iss;
+  if ((int)blockIdx.x + (PT_STAGES - 1) * G < ntiles) iss = __ldg(order + blockIdx.x + (PT_STAGES - 1) * G);
   int it = 0;
-  for (int t = blockIdx.x; t < ntiles; t += G, ++it) {
+  for (int t = blockIdx.x; t < ntiles; t += G, ++it, cur = nxt, iss = iss_nxt) {
     const int stage = it % PT_STAGES;
     if (leader) {
       const int tn = t + (PT_STAGES - 1) * G;
-      if (tn < ntiles) issue_tile((stage + PT_STAGES - 1) % PT_STAGES, tn);
+      if (tn < ntiles) issue_tile((stage + PT_STAGES - 1) % PT_STAGES, iss);
     }
-    const int j = 1 + (t % ntx) * PT_W + lx, k = 1 + (t / ntx) * PT_H + ly;
+    nxt = (t + G < ntiles) ? __ldg(order + t + G) : cur;
+    iss_nxt = (t + PT_STAGES * G < ntiles) ? __ldg(order + t + PT_STAGES * G) : iss;
+    const int j = 1 + cur.x * PT_W + lx, k = 1 + cur.y * PT_H + ly;
     ring.wait(stage, (uint32_t)((it / PT_STAGES) & 1));
     const double* __restrict__ sxa = ring.tile(stage, PA_XAREA);
     const double* __restrict__ sya = ring.tile(stage, PA_YAREA);
@@ -474,7 +486,7 @@ struct CorrectCfg {
 template <int W, int RPT, int STAGES, int CPS>
 __global__ void __launch_bounds__(W* LT_H / RPT, CPS)
     lagrange_correct_tma_kernel(const __grid_constant__ CorrectMaps M, CorrectOut O, int nx, int ny, int pitch,
-                                double dt, int ntx, int ntiles) {
+                                double dt, int ntx, int ntiles, const int2* __restrict__ order) {
   using Cfg = CorrectCfg<W, RPT, STAGES, CPS>;
   constexpr int NT = Cfg::NT, VPT = Cfg::VPT, NVERT = Cfg::NVERT, ROWS = LT_H / RPT, LT_W = W, LT_BW = Cfg::BW, LT_VW = Cfg::VW;
   extern __shared__ unsigned char smem_raw[];
@@ -487,25 +499,30 @@ __global__ void __launch_bounds__(W* LT_H / RPT, CPS)
   const int G = gridDim.x;
   const int jmax = nx + 1, kmax = ny + 1;
   // box corner of tile t in tensor coordinates: element (j,k) is at (j + XOFF, k + 1)
-  auto issue_tile = [&](int stage, int t) {
-    const int j0 = 1 + (t % ntx) * LT_W, k0 = 1 + (t / ntx) * LT_H;
+  auto issue_tile = [&](int stage, int2 xy) {
+    const int j0 = 1 + xy.x * LT_W, k0 = 1 + xy.y * LT_H;
     ring.issue(M.m, stage, j0 - LT_OX + XOFF, k0 - 1 + 1);
   };
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
       const int t = (int)blockIdx.x + s * G;
-      if (t < ntiles) issue_tile(s, t);
+      if (t < ntiles) issue_tile(s, __ldg(order + t));
     }
   }
+  // tile coordinates: host-built order table (tile_order, tma.cuh), fetched one iteration before they are needed
+  int2 cur = __ldg(order + blockIdx.x), nxt = cur, iss = make_int2(0, 0), iss_nxt = iss;
+  if ((int)blockIdx.x + (STAGES - 1) * G < ntiles) iss = __ldg(order + blockIdx.x + (STAGES - 1) * G);
   int it = 0;
-  for (int t = blockIdx.x; t < ntiles; t += G, ++it) {
+  for (int t = blockIdx.x; t < ntiles; t += G, ++it, cur = nxt, iss = iss_nxt) {
     const int stage = it % STAGES;
     if (tid == 0) {
       const int tn = t + (STAGES - 1) * G;  // its stage was released by the barrier that ended iteration it-1
-      if (tn < ntiles) issue_tile((stage + STAGES - 1) % STAGES, tn);
+      if (tn < ntiles) issue_tile((stage + STAGES - 1) % STAGES, iss);
     }
-    const int j0 = 1 + (t % ntx) * LT_W, k0 = 1 + (t / ntx) * LT_H;
+    nxt = (t + G < ntiles) ? __ldg(order + t + G) : cur;
+    iss_nxt = (t + STAGES * G < ntiles) ? __ldg(order + t + STAGES * G) : iss;
+    const int j0 = 1 + cur.x * LT_W, k0 = 1 + cur.y * LT_H;
     ring.wait(stage, (uint32_t)((it / STAGES) & 1));
     const double* __restrict__ sxa = ring.tile(stage, LA_XAREA);
     const double* __restrict__ sya = ring.tile(stage, LA_YAREA);
@@ -621,7 +638,7 @@ static void launch_correct_tma(const CorrectArgs& A, const Grid& g, double dt) {
   const int cap = sm_count() * CPS;
   const int ctas = ntiles < cap ? ntiles : cap;
   lagrange_correct_tma_kernel<W, RPT, STAGES, CPS><<<ctas, Cfg::NT, Cfg::SMEM, stream()>>>(M, O, g.nx, g.ny, g.pitch, dt, ntx,
-                                                                                       ntiles);
+                                                                                       ntiles, tile_order(ntx, nty, LT_W));
 }
 
 // single-call host launchers (lagrange.cu, advec.cu)
@@ -789,7 +806,8 @@ static size_t fuse_timestep(const Op* q, size_t n, size_t i) {
       double* part = partials((size_t)ctas);
       LaunchScope ls("timestep_tma");
       timestep_tma_kernel<true><<<ctas, dim3(BX, BY), TT_SMEM, stream()>>>(M, P, cdx, cdy, d0, e0, p, qv, ss, part, ticket(),
-                                                                          host_scalars(), g.nx, g.ny, g.pitch, ntx, ntiles);
+                                                                          host_scalars(), g.nx, g.ny, g.pitch, ntx, ntiles,
+                                                                          tile_order(ntx, nty, TT_W));
     } else {
     const dim3 grid = persistent_grid(r, 1, g_ctas_per_sm_timestep[0]);
     double* part = partials((size_t)grid.x * grid.y);
@@ -860,9 +878,11 @@ static size_t fuse_predict(const Op* q, size_t n, size_t i) {
       const int ctas = ntiles < cap ? ntiles : cap;
       LaunchScope ls("pdv_predict_tma");
       if (write_ss)
-        pdv_predict_eos_tma_kernel<true><<<ctas, dim3(BX, BY), PT_SMEM, stream()>>>(M, pv.sv[0], p, ss, g.nx, g.ny, g.pitch, ntx, ntiles);
+        pdv_predict_eos_tma_kernel<true><<<ctas, dim3(BX, BY), PT_SMEM, stream()>>>(M, pv.sv[0], p, ss, g.nx, g.ny, g.pitch, ntx, ntiles,
+                                                                                    tile_order(ntx, nty, PT_W));
       else
-        pdv_predict_eos_tma_kernel<false><<<ctas, dim3(BX, BY), PT_SMEM, stream()>>>(M, pv.sv[0], p, ss, g.nx, g.ny, g.pitch, ntx, ntiles);
+        pdv_predict_eos_tma_kernel<false><<<ctas, dim3(BX, BY), PT_SMEM, stream()>>>(M, pv.sv[0], p, ss, g.nx, g.ny, g.pitch, ntx, ntiles,
+                                                                                     tile_order(ntx, nty, PT_W));
     } else {
     const Range r = make_range(1, g.nx, 1, g.ny);
     const dim3 grid = grid_for(r, NR_PRED);

@@ -484,6 +484,31 @@ const CUtensorMap* tensor_map_for(const Grid& g, const double* dev_ptr, int box_
   return m;
 }
 
+namespace {
+std::map<std::tuple<int, int, int>, int2*> g_tile_orders;
+}
+const int2* tile_order(int ntx, int nty, int tw) {
+  constexpr int BAND_COLS = 4096;
+  const int band_tiles = (ntx * tw <= BAND_COLS + 256) ? ntx : (BAND_COLS / tw > 0 ? BAND_COLS / tw : 1);
+  const auto key = std::make_tuple(ntx, nty, band_tiles);
+  auto it = g_tile_orders.find(key);
+  if (it != g_tile_orders.end()) return it->second;
+  std::vector<int2> h;
+  h.reserve((size_t)ntx * nty);
+  for (int x0 = 0; x0 < ntx; x0 += band_tiles) {
+    const int w = (ntx - x0 < band_tiles) ? ntx - x0 : band_tiles;
+    for (int ty = 0; ty < nty; ++ty)
+      for (int tx = x0; tx < x0 + w; ++tx) h.push_back(make_int2(tx, ty));
+  }
+  if ((int)h.size() != ntx * nty) fatal("tile_order: %zu entries for %d x %d tiles", h.size(), ntx, nty);
+  int2* d = nullptr;
+  CLV_CUDA(cudaMalloc(&d, h.size() * sizeof(int2)));
+  CLV_CUDA(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice, R.stream));
+  CLV_CUDA(cudaStreamSynchronize(R.stream));
+  g_tile_orders[key] = d;
+  return d;
+}
+
 // used by halo.cu
 bool chunk_registered() { return C.set; }
 int chunk_nx() { return C.nx; }

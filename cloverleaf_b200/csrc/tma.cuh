@@ -25,6 +25,14 @@ namespace clv {
 // Host: tensor map of `dev_ptr` (a field in the pitched layout of grid g) with a box_w x box_h box; cached.
 const CUtensorMap* tensor_map_for(const Grid& g, const double* dev_ptr, int box_w, int box_h);
 
+// Host: device table of the ntx*nty tile coordinates of a grid of tw-wide tiles, in the order the persistent CTAs walk
+// them (CTA b takes entries b, b+G, b+2G, ...; the kernels fetch an entry one iteration before they need it); cached
+// per shape.  Chunks up to ~4096 cells wide are walked row by row: the CTAs that run at the same time then stream long
+// contiguous row segments and the halo rows shared with the next tile row are still in L2 one tile row later.  Wider
+// chunks are walked down bands of ~4096 columns, which keeps both properties (a 15360-wide chunk walked row by row
+// re-fetched its halo rows from DRAM: ncu showed 1.16x - 2.1x the compulsory reads, against 1.00x - 1.05x at 3840).
+const int2* tile_order(int ntx, int nty, int tw);
+
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
