@@ -428,6 +428,8 @@ def _main():
                               "peak_source": peak_src},
             "kernels": kernels, "cpu_baseline": cpu,
         }
+    # leave the device idle before the ranks part: nothing of ours may still be writing into a peer's memory
+    lib.clover_b200_device_synchronize_()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
