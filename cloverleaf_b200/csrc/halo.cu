@@ -612,7 +612,7 @@ static void p2p_release() {
 // All-reduce of up to 8 doubles over peer memory: every rank drops its values, then the sequence number (release,
 // system scope), into its mailbox in every rank's block; thread r of the single CTA waits for rank r's mailbox and
 // thread 0 folds the values in rank order, so all ranks compute bit-identical results (clover_min: clover.f90:
-// 532-551 MPI_ALLREDUCE(MIN); clover_sum: :506-525).  `in`/`out` are pinned, device-visible host memory.
+// 3641-3657 MPI_ALLREDUCE(MIN); clover_sum: :3621-3639 MPI_REDUCE(SUM) to rank 0).  `in`/`out` are pinned, device-visible host memory.
 __global__ void __launch_bounds__(P2P_MAX_RANKS)
     p2p_allreduce_kernel(unsigned char** all, int nranks, int rank, const double* in, double* out, int n, int is_min,
                          unsigned long long seq) {
