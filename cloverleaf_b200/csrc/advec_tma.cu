@@ -446,9 +446,6 @@ void run_advec_cell_tma(const Grid& g, int dir, int sweep, double* vertexdx, dou
   double* mf = dir == 1 ? dev(g, mass_flux_x, XFACE, OUT_FULL) : dev(g, mass_flux_y, YFACE, OUT_FULL);
   const double* in[CA_NARR] = {vol, fx, fy, d_old, e_old};
   CellMaps M;
-  static int cx = -1, cy = -1;
-  if (cx < 0) cx = getenv("CLOVER_B200_CX_CFG") ? atoi(getenv("CLOVER_B200_CX_CFG")) : 0;
-  if (cy < 0) cy = getenv("CLOVER_B200_CY_CFG") ? atoi(getenv("CLOVER_B200_CY_CFG")) : 0;
   LaunchScope ls(dir == 1 ? "advec_cell_x_tma" : "advec_cell_y_tma");
 #define CLV_CELL(DIR, TX, TY, RPT, ST, CPS)                                                                \
   do {                                                                                                     \
@@ -457,23 +454,11 @@ void run_advec_cell_tma(const Grid& g, int dir, int sweep, double* vertexdx, dou
     if (sweep == 1) launch_cell<DIR, 1, TX, TY, RPT, ST, CPS>(g, M, d_old, d_new, e_old, e_new, mf, vd);   \
     else            launch_cell<DIR, 2, TX, TY, RPT, ST, CPS>(g, M, d_old, d_new, e_old, e_new, mf, vd);   \
   } while (0)
-  if (dir == 1) {
-    switch (cx) {
-      case 1: CLV_CELL(1, 64, 4, 2, 2, 2); break;
-      case 2: CLV_CELL(1, 64, 4, 2, 3, 2); break;
-      case 3: CLV_CELL(1, 64, 4, 1, 2, 4); break;
-      case 4: CLV_CELL(1, 64, 8, 1, 2, 2); break;
-      default: CLV_CELL(1, 64, 4, 2, 2, 3); break;  // measured best on B200 (0.181 ms at 3840^2)
-    }
-  } else {
-    switch (cy) {
-      case 1: CLV_CELL(2, 32, 8, 3, 2, 2); break;
-      case 2: CLV_CELL(2, 32, 8, 2, 2, 2); break;
-      case 3: CLV_CELL(2, 32, 8, 4, 2, 2); break;
-      case 4: CLV_CELL(2, 64, 4, 3, 2, 2); break;
-      default: CLV_CELL(2, 32, 8, 2, 2, 3); break;  // measured best on B200 (0.211 ms at 3840^2)
-    }
-  }
+  // <thread grid TX x TY, rows per thread, ring stages, CTAs per SM>; measured on B200 at 3840^2:
+  //   x: <64,4,2,2,3> 0.181 ms, <64,4,2,2,2> 0.221, <64,4,2,3,2> 0.224, <64,4,1,2,4> 0.236, <64,8,1,2,2> 0.236
+  //   y: <32,8,2,2,3> 0.211 ms, <32,8,3,2,2> 0.217, <32,8,2,2,2> 0.247, <64,4,3,2,2> 0.245, <32,8,4,2,2> 0.342
+  if (dir == 1) CLV_CELL(1, 64, 4, 2, 2, 3);
+  else          CLV_CELL(2, 32, 8, 2, 2, 3);
 #undef CLV_CELL
   swap_alt(density1);
   swap_alt(energy1);
@@ -499,9 +484,6 @@ void run_advec_mom_tma(const Grid& g, int dirn, int sweep, double* vel_a, double
   const double* in[MA_NARR] = {vol, d1, mf, va_old, vb_old, mom_sweep == 1 ? fy : fx};
   MomMaps M;
   LaunchScope ls(dirn == 1 ? "advec_mom_x_tma" : "advec_mom_y_tma");
-  static int cx = -1, cy = -1;
-  if (cx < 0) cx = getenv("CLOVER_B200_MX_CFG") ? atoi(getenv("CLOVER_B200_MX_CFG")) : 0;
-  if (cy < 0) cy = getenv("CLOVER_B200_MY_CFG") ? atoi(getenv("CLOVER_B200_MY_CFG")) : 0;
 #define CLV_MOM(DIR, TX, TY, RPT, ST, CPS)                                                             \
   do {                                                                                                 \
     using Cfg = MomCfg<DIR, TX, TY, RPT, ST, CPS>;                                                     \
@@ -509,25 +491,11 @@ void run_advec_mom_tma(const Grid& g, int dirn, int sweep, double* vel_a, double
     if (mom_sweep <= 2) launch_mom<DIR, DIR, TX, TY, RPT, ST, CPS>(g, M, va_old, va_new, vb_old, vb_new, cd);     \
     else                launch_mom<DIR, DIR + 2, TX, TY, RPT, ST, CPS>(g, M, va_old, va_new, vb_old, vb_new, cd); \
   } while (0)
-  if (dirn == 1) {
-    switch (cx) {
-      case 1: CLV_MOM(1, 64, 4, 2, 3, 2); break;
-      case 2: CLV_MOM(1, 64, 4, 1, 2, 3); break;
-      case 3: CLV_MOM(1, 64, 4, 1, 2, 4); break;
-      case 4: CLV_MOM(1, 64, 8, 1, 2, 2); break;
-      case 5: CLV_MOM(1, 64, 2, 4, 2, 2); break;
-      default: CLV_MOM(1, 64, 4, 2, 2, 2); break;
-    }
-  } else {
-    switch (cy) {
-      case 1: CLV_MOM(2, 32, 8, 2, 2, 3); break;
-      case 2: CLV_MOM(2, 32, 8, 2, 2, 2); break;
-      case 3: CLV_MOM(2, 64, 4, 4, 2, 1); break;
-      case 4: CLV_MOM(2, 32, 16, 1, 2, 2); break;
-      case 5: CLV_MOM(2, 32, 4, 4, 2, 3); break;
-      default: CLV_MOM(2, 32, 8, 3, 2, 2); break;  // measured best on B200 (0.214 ms at 3840^2)
-    }
-  }
+  // <thread grid TX x TY, rows per thread, ring stages, CTAs per SM>; measured on B200 at 3840^2:
+  //   x: <64,4,2,2,2> 0.211 ms, <64,4,1,2,4> 0.216, <64,8,1,2,2> 0.221, <64,4,2,3,2> 0.229, <64,2,4,2,2> 0.305
+  //   y: <32,8,3,2,2> 0.214 ms, <32,8,2,2,3> 0.236, <32,4,4,2,3> 0.240, <32,8,2,2,2> 0.247, <32,16,1,2,2> 0.255
+  if (dirn == 1) CLV_MOM(1, 64, 4, 2, 2, 2);
+  else           CLV_MOM(2, 32, 8, 3, 2, 2);
 #undef CLV_MOM
   swap_alt(vel_a);
   swap_alt(vel_b);
