@@ -91,6 +91,7 @@ struct Backend {
   void (*x_min)(dp) = nullptr;
   void (*x_sum)(dp, ip) = nullptr;
   void (*x_sync_to_host)(ip) = nullptr;
+  void (*x_download)(dp) = nullptr;  // one array device -> host (GPU backends only)
   void (*x_forget)(dp) = nullptr;
 };
 
@@ -230,7 +231,10 @@ struct clover_driver {
   void advection();
   void reset_field();
   void field_summary();
+  void visit();
   bool hydro_step();
+  std::string visit_dir;  // where visit() writes; empty = visit output disabled (the deck's visit_frequency still parses)
+  bool visit_first_call = true;
 };
 
 bool clover_driver::load_backend(const char* path) {
@@ -268,6 +272,7 @@ bool clover_driver::load_backend(const char* path) {
   sym(h, "clover_b200_min_", be.x_min, false, ignore);
   sym(h, "clover_b200_sum_", be.x_sum, false, ignore);
   sym(h, "clover_b200_sync_to_host_", be.x_sync_to_host, false, ignore);
+  sym(h, "clover_b200_download_", be.x_download, false, ignore);
   sym(h, "clover_b200_forget_", be.x_forget, false, ignore);
   if (!e.empty()) {
     error = "backend " + std::string(path) + ":" + e;
@@ -518,6 +523,7 @@ void clover_driver::start() {
   update_halo(fields, 2);
   log("\n Problem initialised and generated\n");
   field_summary();
+  if (deck.visit_frequency != 0) visit();  // start.f90:145
 }
 
 void clover_driver::exchange(const int* fields, int depth) {
@@ -805,6 +811,101 @@ void clover_driver::field_summary() {
   }
 }
 
+// Fortran `E12.4` edit descriptor: 0.dddd mantissa, two-digit exponent, right-justified in 12 columns
+static void fortran_e12_4(FILE* f, double v) {
+  if (v == 0.0 || !std::isfinite(v)) {
+    if (v == 0.0) fprintf(f, "%s\n", std::signbit(v) ? " -0.0000E+00" : "  0.0000E+00");
+    else fprintf(f, "%12s\n", std::isnan(v) ? "NaN" : (v > 0 ? "Infinity" : "-Infinity"));
+    return;
+  }
+  int e = (int)std::floor(std::log10(std::fabs(v))) + 1;
+  double m = std::fabs(v) / std::pow(10.0, e);
+  long digits = std::lround(m * 1.0e4);
+  if (digits >= 10000) { digits = 1000; e += 1; }   // 0.99996 rounds up to 1.0000 -> 0.1000E+(e+1)
+  if (digits < 1000) { digits *= 10; e -= 1; }       // log10 landed one decade high
+  char buf[32];
+  snprintf(buf, sizeof buf, "%s0.%04ldE%c%02d", v < 0 ? "-" : "", digits, e < 0 ? '-' : '+', e < 0 ? -e : e);
+  fprintf(f, "%12s\n", buf);
+}
+
+void clover_driver::visit() {
+  // visit.f90:25-180: refresh pressure and viscosity, then one ASCII VTK rectilinear-grid file per chunk and
+  // an index file `clover.visit`.  Disabled unless an output directory was given (clover_driver_set_visit).
+  if (visit_dir.empty()) return;
+  const bool boss = (comm_mode == 0) || rank == 0;
+  const std::string index = visit_dir + "/clover.visit";
+  if (boss && visit_first_call) {  // :52-60
+    FILE* u = fopen(index.c_str(), "w");
+    if (!u) { error = "visit: cannot write " + index; return; }
+    fprintf(u, "!NBLOCKS %5d\n", nchunks * deck.tiles_per_chunk);
+    fclose(u);
+  }
+  visit_first_call = false;
+  for (Chunk& c : chunks) ideal_gas(c, false);  // :65-67
+  int fields[NUM_FIELDS] = {0};
+  fields[FIELD_PRESSURE - 1] = 1; fields[FIELD_XVEL0 - 1] = 1; fields[FIELD_YVEL0 - 1] = 1;
+  update_halo(fields, 1);                        // :70-74
+  for (Chunk& c : chunks)                         // :77
+    be.viscosity(&c.x_min, &c.x_max, &c.y_min, &c.y_max, c.celldx, c.celldy, c.density0, c.pressure,
+                 c.viscosity, c.xvel0, c.yvel0);
+  // a GPU backend keeps the fields on the device: bring the six dumped ones back (the D2H path of visit)
+  if (be.x_download)
+    for (Chunk& c : chunks)
+      for (dp a : {c.density0, c.energy0, c.pressure, c.viscosity, c.xvel0, c.yvel0}) be.x_download(a);
+  auto vtk_name = [&](int task) {
+    char b[64];
+    snprintf(b, sizeof b, "clover.%05d.%05d.%05d.vtk", task, 1, step);  // i6 of n+100000 with the '1' -> '.'
+    return std::string(b);
+  };
+  if (boss) {  // :81-99
+    FILE* u = fopen(index.c_str(), "a");
+    if (!u) { error = "visit: cannot append to " + index; return; }
+    for (int task = 0; task < nchunks; ++task) fprintf(u, "%s\n", vtk_name(task).c_str());
+    fclose(u);
+  }
+  for (Chunk& c : chunks) {  // :103-177
+    const int nxc = c.x_max - c.x_min + 1, nyc = c.y_max - c.y_min + 1, nxv = nxc + 1, nyv = nyc + 1;
+    const std::string fn = visit_dir + "/" + vtk_name(c.id - 1);
+    FILE* u = fopen(fn.c_str(), "w");
+    if (!u) { error = "visit: cannot write " + fn; return; }
+    const size_t rc = (size_t)(c.x_max + 4), rv = (size_t)(c.x_max + 5);  // cell / vertex row lengths (lower bound -1)
+    auto cell = [&](dp a, int j, int k) { return a[(size_t)(k + 1) * rc + (size_t)(j + 1)]; };
+    auto vert = [&](dp a, int j, int k) { return a[(size_t)(k + 1) * rv + (size_t)(j + 1)]; };
+    fprintf(u, "# vtk DataFile Version 3.0\nvtk output\nASCII\nDATASET RECTILINEAR_GRID\n");
+    fprintf(u, "DIMENSIONS%12d%12d 1\n", nxv, nyv);
+    fprintf(u, "X_COORDINATES %5d double\n", nxv);
+    for (int j = c.x_min; j <= c.x_max + 1; ++j) fortran_e12_4(u, c.vertexx[j + 1]);
+    fprintf(u, "Y_COORDINATES %5d double\n", nyv);
+    for (int k = c.y_min; k <= c.y_max + 1; ++k) fortran_e12_4(u, c.vertexy[k + 1]);
+    fprintf(u, "Z_COORDINATES 1 double\n0\n");
+    fprintf(u, "CELL_DATA %20d\nFIELD FieldData 4\n", nxc * nyc);
+    const struct { const char* name; dp a; bool clip; } cells[4] = {
+        {"density", c.density0, false}, {"energy", c.energy0, false}, {"pressure", c.pressure, false},
+        {"viscosity", c.viscosity, true}};
+    for (const auto& fld : cells) {
+      fprintf(u, "%s 1 %20d double\n", fld.name, nxc * nyc);
+      for (int k = c.y_min; k <= c.y_max; ++k)
+        for (int j = c.x_min; j <= c.x_max; ++j) {
+          double v = cell(fld.a, j, k);
+          if (fld.clip && !(v > 0.00000001)) v = 0.0;  // :146-147
+          fortran_e12_4(u, v);
+        }
+    }
+    fprintf(u, "POINT_DATA %20d\nFIELD FieldData 2\n", nxv * nyv);
+    const struct { const char* name; dp a; } verts[2] = {{"x_vel", c.xvel0}, {"y_vel", c.yvel0}};
+    for (const auto& fld : verts) {
+      fprintf(u, "%s 1 %20d double\n", fld.name, nxv * nyv);
+      for (int k = c.y_min; k <= c.y_max + 1; ++k)
+        for (int j = c.x_min; j <= c.x_max + 1; ++j) {
+          double v = vert(fld.a, j, k);
+          if (!(std::fabs(v) > 0.00000001)) v = 0.0;  // :155-157, :164-166
+          fortran_e12_4(u, v);
+        }
+    }
+    fclose(u);
+  }
+}
+
 bool clover_driver::hydro_step() {
   // hydro.f90:48-99 (one trip of the DO loop); returns false once complete
   if (complete) return false;
@@ -820,9 +921,11 @@ bool clover_driver::hydro_step() {
   advect_x = !advect_x;
   time = time + dt;
   if (deck.summary_frequency != 0 && step % deck.summary_frequency == 0) field_summary();
+  if (deck.visit_frequency != 0 && step % deck.visit_frequency == 0) visit();  // hydro.f90:73-75
   if (time + g_small > deck.end_time || step >= deck.end_step) {
     complete = true;
     field_summary();
+    if (deck.visit_frequency != 0) visit();  // hydro.f90:88
     log("\n Calculation complete\n Clover is finishing\n");
     return false;
   }
@@ -858,6 +961,11 @@ void clover_driver_set_comm_callbacks(clover_driver* d, void (*sendrecv)(int, co
 void clover_driver_set_end_step(clover_driver* d, int end_step) { d->deck.end_step = end_step; }
 void clover_driver_set_end_time(clover_driver* d, double end_time) { d->deck.end_time = end_time; }
 void clover_driver_set_summary_frequency(clover_driver* d, int f) { d->deck.summary_frequency = f; }
+// visit.f90 output: directory for clover.visit / *.vtk and the dump frequency in steps (0 keeps the deck's value)
+void clover_driver_set_visit(clover_driver* d, const char* dir, int frequency) {
+  d->visit_dir = dir ? dir : "";
+  if (frequency > 0) d->deck.visit_frequency = frequency;
+}
 
 int clover_driver_start(clover_driver* d) {
   if (!d->error.empty()) return -1;

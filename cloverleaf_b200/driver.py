@@ -32,6 +32,7 @@ def _driver_lib():
             ("clover_driver_set_end_step", None, [vp, ci]),
             ("clover_driver_set_end_time", None, [vp, cd]),
             ("clover_driver_set_summary_frequency", None, [vp, ci]),
+            ("clover_driver_set_visit", None, [vp, cs, ci]),
             ("clover_driver_start", ci, [vp]),
             ("clover_driver_run", ci, [vp, ci]),
             ("clover_driver_field_summary", None, [vp]),
@@ -100,6 +101,11 @@ class Driver:
     SENDRECV = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                 ctypes.POINTER(ctypes.c_double), ctypes.c_int)
     ALLREDUCE = ctypes.CFUNCTYPE(None, ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_int)
+
+    def set_visit(self, directory, frequency=0):
+        """visit.f90 output (clover.visit + one ASCII VTK file per chunk and dump) into `directory`, every
+        `frequency` steps (0: the deck's visit_frequency).  Call before start()."""
+        self._L.clover_driver_set_visit(self._h, str(directory).encode(), int(frequency))
 
     def set_comm_callbacks(self, sendrecv, allreduce):
         """comm_mode=2: sendrecv(peer, snd, rcv, count) and allreduce(values, n, op[0 min,1 sum]) are
