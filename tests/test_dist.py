@@ -85,10 +85,11 @@ def _free_port():
     return p
 
 
-def _run_world(tmp_path, world, backend, lib, nx, ny, steps):
+def _run_world(tmp_path, world, backend, lib, nx, ny, steps, extra_env=None):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, CLV_ROOT=ROOT, CLV_BACKEND=backend, CLV_LIB=lib, CLV_NX=str(nx), CLV_NY=str(ny),
+    env = dict(os.environ, **(extra_env or {}))
+    env = dict(env, CLV_ROOT=ROOT, CLV_BACKEND=backend, CLV_LIB=lib, CLV_NX=str(nx), CLV_NY=str(ny),
                CLV_STEPS=str(steps), CLV_OUT=str(tmp_path), OMP_NUM_THREADS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
@@ -142,3 +143,17 @@ def test_nccl_ranks_match_single_gpu(tmp_path, world):
     for a, b in zip(ranks[0]["summaries"], s1):
         for k in ("volume", "mass", "ie", "ke", "pressure"):
             assert abs(a[k] - b[k]) <= 1e-10 * max(abs(b[k]), 1e-300)
+
+
+@pytest.mark.gpu
+def test_nccl_transport_matches_single_gpu(tmp_path):
+    """The fallback transport (ncclSend/ncclRecv + ncclAllReduce, CLOVER_B200_P2P=0) against the same oracle run."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import cloverleaf_b200
+    nx, ny, steps = 256, 192, 30
+    ranks = _run_world(tmp_path, 2, "nccl", cloverleaf_b200.LIB_B200, nx, ny, steps,
+                       extra_env={"CLOVER_B200_P2P": "0"})
+    dt1, _ = _single(ORACLE_PORT, nx, ny, steps)
+    for r in ranks:
+        assert r["dt"] == dt1, "rank %d: dt differs from the oracle's single-chunk run" % r["rank"]
