@@ -9,7 +9,9 @@ flux_calc, advection, reset_field, + field_summary every 10th step), driven by t
 of the Fortran driver through the reference's `*_kernel_c_` C-ABI.
 
 N > 1 (torchrun, one rank per GPU): the same mesh is decomposed by clover_decompose into N chunks,
-one per GPU (strong scaling); halos travel device->device over NCCL, dt by ncclAllReduce(min).
+one per GPU (strong scaling).  Data path: the library's own kernels over peer memory (NVLink/NVSwitch,
+cudaIpc-mapped exchange blocks; csrc/halo.cu) for the halos, the dt minimum and the summary sums; NCCL is
+used for bootstrap only (and as the fallback transport, CLOVER_B200_P2P=0).
 
 Printed JSON (one line, rank 0): see the contract in the task statement.  Extra keys:
   value        device-timed (CUDA events on the library's stream), state resident in HBM
@@ -19,6 +21,9 @@ Printed JSON (one line, rank 0): see the contract in the task statement.  Extra 
   roofline     dominant kernel: algorithmic bytes per launch / mean launch duration (CUDA events)
   step_roofline  whole step: 856 B x cells / ms_per_step against the same peak
   cpu_baseline the reference's own C kernels (oracle/_ref, OpenMP, all host cores) on a bounded sample
+  parity       every dt of the run (warm-up, timed and profiled steps) compared BIT FOR BIT, and every summary row
+               to 1e-10, with the committed trace of the reference's C kernels for this deck (tests/golden/);
+               a mismatch makes the run exit non-zero.  At N > 1 this is the multi-GPU parity proof.
 """
 import argparse
 import ctypes
@@ -31,7 +36,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = os.environ.get("CLV_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+os.environ.setdefault("NCCL_DEBUG", "WARN")  # the caller's setting wins; stdout is protected by the dup2 in main()
 
 ALG_BYTES_PER_CELL_STEP = 856.0  # 107 fp64 array passes
 # Array passes per launch: (own, survey).  `own` = the fp64 array passes the kernel itself has to move (each input
@@ -177,6 +182,34 @@ def cpu_reference_run(deck, steps, warmup, budget_s=150.0):
                     os.path.basename(ref), cores))
 
 
+GOLDEN_FOR = {"clover_bm16_short.in": "bm16_short_3840_full.json", "clover_bm_short.in": "bm_short_960_full.json",
+              "clover_bm.in": "tp3_bm_960_full.json", "clover_bm16.in": "tp5_bm16_3840_full.json",
+              "clover_bm64_short.in": "bm64_short_7680_first10.json",
+              "clover_bm256_short.in": "bm256_short_15360_first10.json"}
+
+
+def parity_check(deck_name, dts, summaries):
+    """dt trace and summary rows of a run that started at step 1 against the committed reference trace."""
+    path = os.path.join(ROOT, "tests", "golden", GOLDEN_FOR.get(deck_name, "?"))
+    if not os.path.exists(path):
+        return {"golden": None, "dt_steps_checked": 0, "dt_bit_identical": None, "summary_max_rel": None}
+    G = json.load(open(path))
+    n = min(len(dts), len(G["dt"]))
+    bad = next((i for i in range(n) if dts[i] != G["dt"][i]), None)
+    gold = {int(r["step"]): r for r in G["summaries"]}
+    worst, rows = 0.0, 0
+    for r in summaries:
+        g = gold.get(int(r["step"]))
+        if g is None or int(r["step"]) > n:
+            continue
+        rows += 1
+        for k in ("volume", "mass", "pressure", "ie", "ke", "total"):
+            worst = max(worst, abs(r[k] - g[k]) / max(abs(g[k]), 1e-300))
+    return {"golden": "tests/golden/" + os.path.basename(path), "dt_steps_checked": n, "dt_bit_identical": bad is None,
+            "first_dt_mismatch_step": None if bad is None else bad + 1, "summary_rows_checked": rows,
+            "summary_max_rel": worst, "summary_tol": 1e-10, "ok": bad is None and worst <= 1e-10}
+
+
 def main():
     # Libraries underneath (NCCL: "NCCL version ..." when NCCL_DEBUG is set) write to fd 1; the contract is ONE
     # JSON line on stdout, so everything but that line goes to stderr.
@@ -190,6 +223,10 @@ def main():
         os.dup2(json_fd, 1)
     if line is not None:
         os.write(json_fd, (json.dumps(line) + "\n").encode())
+        par = line.get("parity")
+        if par and par.get("ok") is False:
+            sys.stderr.write("bench.py: PARITY FAILURE against %s: %r\n" % (par.get("golden"), par))
+            sys.exit(3)
 
 
 def _main():
@@ -354,6 +391,15 @@ def _main():
                             "launch time; the reference calls it replaces would move reference_calls_alg_bytes"}
     step_gbs = ALG_BYTES_PER_CELL_STEP * cells / world / (ms_per_step * 1e-3) / 1e9
     chunks = "%dx%d (clover_decompose)" % (d.grid()["chunk_x"], d.grid()["chunk_y"])
+    # parity of everything this driver instance ran (warm-up + timed + profiled steps, from step 1)
+    parity = parity_check(args.deck, d.dts().tolist(), d.summaries())
+    if dist is not None:
+        import torch
+        t = torch.tensor([0.0 if parity.get("ok") is False else 1.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)  # every rank checked its own copy of the trace
+        if float(t.item()) == 0.0:
+            parity["ok"] = False
+        parity["ranks_checked"] = world
     d.close()
 
     # ---- end to end from host arrays (same C-ABI, resident mode, copies inside the timed region)
@@ -426,7 +472,7 @@ def _main():
                               "achieved": round(step_gbs, 1), "peak": peak, "unit": "GB/s",
                               "frac": round(step_gbs / peak, 4), "frac_of_8TBs_nominal": round(step_gbs / 8000.0, 4),
                               "peak_source": peak_src},
-            "kernels": kernels, "cpu_baseline": cpu,
+            "kernels": kernels, "cpu_baseline": cpu, "parity": parity,
         }
     # leave the device idle before the ranks part: nothing of ours may still be writing into a peer's memory
     lib.clover_b200_device_synchronize_()

@@ -851,7 +851,8 @@ void clover_driver::visit() {
   // a GPU backend keeps the fields on the device: bring the six dumped ones back (the D2H path of visit)
   if (be.x_download)
     for (Chunk& c : chunks)
-      for (dp a : {c.density0, c.energy0, c.pressure, c.viscosity, c.xvel0, c.yvel0}) be.x_download(a);
+      for (dp a : {c.density0, c.energy0, c.pressure, c.viscosity, c.xvel0, c.yvel0, c.vertexx, c.vertexy})
+        be.x_download(a);  // vertexx/vertexy: visit.f90:127,131 (already on the host after initialise_chunk; cheap)
   auto vtk_name = [&](int task) {
     char b[64];
     snprintf(b, sizeof b, "clover.%05d.%05d.%05d.vtk", task, 1, step);  // i6 of n+100000 with the '1' -> '.'
@@ -1047,7 +1048,15 @@ double* clover_driver_field(clover_driver* d, int idx, const char* name) {
 }
 
 void clover_driver_sync_to_host(clover_driver* d) {
-  if (d->be.x_sync_to_host) {
+  // every local chunk's 15 hydro fields and 2-D geometry, by address (the backend's sync_to_host_ knows only the
+  // one chunk registered for exchange, which is not enough with several chunks per process)
+  if (d->be.x_download) {
+    for (Chunk& c : d->chunks)
+      for (dp a : {c.density0, c.density1, c.energy0, c.energy1, c.pressure, c.viscosity, c.soundspeed, c.xvel0,
+                   c.xvel1, c.yvel0, c.yvel1, c.vol_flux_x, c.vol_flux_y, c.mass_flux_x, c.mass_flux_y, c.volume,
+                   c.xarea, c.yarea})
+        d->be.x_download(a);
+  } else if (d->be.x_sync_to_host) {
     int fields[NUM_FIELDS];
     for (int i = 0; i < NUM_FIELDS; ++i) fields[i] = 1;
     d->be.x_sync_to_host(fields);

@@ -985,6 +985,12 @@ void initialise_chunk_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, doub
     LaunchScope ls("initialise_chunk_2d");
     init_chunk_2d_kernel<<<grid, block, 0, stream()>>>(g.nx, g.ny, g.pitch, *dx, *dy, vol, xa, ya);
   }
+  // The eight 1-D geometry arrays never change again and host code reads them (visit.f90:127,131 writes
+  // vertexx/vertexy into the VTK files): they always come back to the host, resident mode or not.  The three 2-D
+  // ones (volume, xarea, yarea) stay on the device; clover_b200_download_ brings one back on request.
+  if (is_resident()) {
+    for (double* a : {vertexx, vertexdx, vertexy, vertexdy, cellx, celldx, celly, celldy}) clover_b200_download_(a);
+  }
   finish();
 }
 

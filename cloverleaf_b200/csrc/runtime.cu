@@ -347,6 +347,9 @@ void swap_buffers(const double* host_a, const double* host_b) {
   Entry &x = a->second, &y = b->second;
   if (x.kind != y.kind || x.nx != y.nx || x.ny != y.ny) fatal("swap_buffers: shape mismatch");
   if (x.lazy_src || y.lazy_src) fatal("swap_buffers with a lazy copy pending");
+  // pending copies that READ one of the two arrays must see its contents from before the swap
+  materialize_dependents(host_a);
+  materialize_dependents(host_b);
   std::swap(x.d, y.d);
 }
 
@@ -642,7 +645,7 @@ void clover_b200_download_(double* host) {
   flush_deferred();
   join_side();
   auto it = R.arrays.find(host);
-  if (it == R.arrays.end()) fatal("download of an array the library has never seen");
+  if (it == R.arrays.end()) return;  // never seen by a kernel: the host copy is the only copy, nothing to bring back
   materialize(it->second);
   download(it->second, host);
   CLV_CUDA(cudaStreamSynchronize(R.stream));

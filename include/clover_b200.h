@@ -11,7 +11,9 @@
  *
  * Part 2 is the small extension a GPU backend needs and the reference ABI has no word for:
  * residency control, host synchronisation, and the replacement of clover_exchange / clover_min /
- * clover_sum (clover.f90:348-500, :3621-3709) by device-side pack + NCCL.
+ * clover_sum (clover.f90:348-500, :3621-3709) by the library's own kernels over peer memory
+ * (NVLink / NVSwitch, cudaIpc-mapped exchange blocks); NCCL bootstraps the ranks and is the fallback
+ * transport (ncclSend/ncclRecv/ncclAllReduce) where cudaIpc is unavailable or CLOVER_B200_P2P=0.
  *
  * Errors: the reference ABI has no status channel.  Any CUDA / NCCL failure prints a diagnostic
  * to stderr and calls abort(); nothing here ever falls back to a CPU path.
@@ -189,12 +191,19 @@ void clover_b200_set_tma_(int *on);
 void clover_b200_invalidate_(void);
 /* Forget the mirror of ONE host array (call before the host frees / re-uses that address). */
 void clover_b200_forget_(double *host_array);
-/* Re-upload one array from its host copy (same effect as invalidate for that array only). */
+/* Re-upload one array from its host copy (same effect as invalidate for that array only).  An address no
+ * kernel has seen yet has no mirror: nothing to do, its first use uploads it.  NOTE (deferred execution): a
+ * first-use upload happens when the recorded stretch RUNS, not when the kernel entry point was called -- host
+ * code that writes an array after passing it to a kernel must call clover_b200_device_synchronize_ first
+ * (CloverLeaf never does this: every array is written by kernels only after start.f90). */
 void clover_b200_upload_(double *host_array);
-/* Copy one array (any host address the library has seen) back to the host. */
+/* Copy one array back to the host (by host address; works for the 2-D fields, the 2-D geometry volume / xarea /
+ * yarea and the 1-D geometry).  An address no kernel has seen yet is left alone: the host copy is the only copy. */
 void clover_b200_download_(double *host_array);
 /* Copy back the fields of the registered chunk selected by the 15-entry mask (ids of
- * data.f90:51-66); this is the hook visit.f90 / a debugger needs. */
+ * data.f90:51-66); this is the hook visit.f90:65-77 / a debugger needs for the hydro fields.  The 1-D geometry
+ * visit.f90:127,131 also reads (vertexx, vertexy) needs no hook: initialise_chunk_kernel_c_ always leaves the
+ * eight 1-D geometry arrays up to date on the host as well as on the device. */
 void clover_b200_sync_to_host_(int *fields);
 /* Block until all device work issued so far has finished. */
 void clover_b200_device_synchronize_(void);
@@ -215,15 +224,20 @@ void clover_b200_register_chunk_(int *xmin, int *xmax, int *ymin, int *ymax, int
 void clover_b200_comm_get_unique_id_(char *id128);
 void clover_b200_comm_init_(int *nranks, int *rank, char *id128);
 
-/* clover_exchange (clover.f90:348-500): device pack of all requested fields per face ->
- * ncclSend/ncclRecv with the face neighbours (left/right phase, then bottom/top phase so the
- * corners propagate) -> device unpack.  Buffer layout inside a message is the reference's
- * (per-field offset = running sum of depth*(edge+5), clover.f90:368-375). */
+/* clover_exchange (clover.f90:348-500).  Default transport (csrc/halo.cu): ONE kernel packs the strips of all
+ * requested fields (message layout = the reference's: per-field offset = running sum of depth*(edge+5),
+ * clover.f90:368-375) straight into the face neighbours' receive slots and the depth x depth corner blocks into
+ * the diagonal neighbours' slots through peer memory, publishes a sequence number (st.release.sys), waits for
+ * its own neighbours' (ld.acquire.sys, bounded: a peer that never arrives makes the kernel trap and the host
+ * abort with a diagnostic) and unpacks.  The reference obtains the corners by running left/right before
+ * bottom/top; the values that land in the corner cells are identical (tests/test_dist.py, bench.py `parity`).
+ * Fallback transport: device pack -> ncclSend/ncclRecv (left/right phase, then bottom/top) -> device unpack. */
 void clover_b200_exchange_(int *fields, int *depth);
-/* clover_min (clover.f90:3640-3656): ncclAllReduce(min) of one double, result on every rank. */
+/* clover_min (clover.f90:3640-3656): minimum of one double over all ranks, result on every rank (peer-memory
+ * mailboxes folded in rank order; fallback ncclAllReduce(min)). */
 void clover_b200_min_(double *value);
-/* clover_sum (clover.f90:3621-3637), n values at once: ncclAllReduce(sum); result on every rank
- * (the reference reduces to rank 0 only). */
+/* clover_sum (clover.f90:3621-3637), n values at once, result on every rank (the reference reduces to rank 0
+ * only); folded in rank order, so every rank holds bit-identical sums (fallback ncclAllReduce(sum)). */
 void clover_b200_sum_(double *values, int *n);
 
 /* Accounting for bench.py: kernels launched so far by this library, and (when enabled with

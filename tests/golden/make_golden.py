@@ -12,7 +12,13 @@ import json
 import os
 import sys
 
-os.environ["OMP_NUM_THREADS"] = "1"
+# --threads N: dt (a min) and every field are independent of the OpenMP thread count (elementwise kernels);
+# only the summed quantities move in the last digits (sum order), far inside the 1e-10 bar.  The long/huge
+# cases below are generated with all cores; the small ones keep 1 thread.
+_thr = "1"
+if "--threads" in sys.argv:
+    _thr = sys.argv[sys.argv.index("--threads") + 1]
+os.environ["OMP_NUM_THREADS"] = _thr
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
@@ -30,13 +36,29 @@ def record(name, deck, nchunks=1, end_step=None, fields=False):
     d = Driver(deck, REF, nchunks=nchunks, end_step=end_step)
     d.run()
     G = dict(deck=deck, nchunks=nchunks, end_step=end_step, steps=d.step, dt=d.dts().tolist(),
-             summaries=d.summaries(), source="oracle/_ref/libclover_ref_c.so (reference C kernels), 1 thread")
+             summaries=d.summaries(),
+             source="oracle/_ref/libclover_ref_c.so (reference C kernels), %s thread(s)" % os.environ["OMP_NUM_THREADS"])
     with open(os.path.join(HERE, name + ".json"), "w") as f:
         json.dump(G, f, indent=0)
     print(name, "steps", d.step, "ke", repr(d.summaries()[-1]["ke"]))
 
 
+def main_only(which):
+    """The long (tp3, tp5) and huge (bm64, bm256) cases of BASELINE.json's configs, one at a time:
+    python tests/golden/make_golden.py --threads 8 --only tp3_bm_960_full"""
+    cases = {
+        "tp3_bm_960_full": lambda: record("tp3_bm_960_full", deck_text("clover_bm.in")),
+        "tp5_bm16_3840_full": lambda: record("tp5_bm16_3840_full", deck_text("clover_bm16.in")),
+        "bm64_short_7680_first10": lambda: record("bm64_short_7680_first10", deck_text("clover_bm64_short.in"), end_step=10),
+        "bm256_short_15360_first10": lambda: record("bm256_short_15360_first10", deck_text("clover_bm256_short.in"), end_step=10),
+    }
+    cases[which]()
+
+
 if __name__ == "__main__":
+    if "--only" in sys.argv:
+        main_only(sys.argv[sys.argv.index("--only") + 1])
+        sys.exit(0)
     bm = deck_text("clover_bm_short.in")
     record("tp1", deck_text("clover_tp1.in"))
     record("bm_short_96", shrink(bm, 96))
