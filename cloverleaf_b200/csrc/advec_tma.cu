@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(TX* TY, CPS)
     advec_mom_tma_kernel(const __grid_constant__ MomMaps M, const double* __restrict__ va_old, double* __restrict__ va_new,
                          const double* __restrict__ vb_old, double* __restrict__ vb_new,
                          const double* __restrict__ celld, int nx, int ny, int pitch, int ntx, int ntiles,
-                        const int2* __restrict__ order) {
+                        const int2* __restrict__ order, int dep_start) {
   using Cfg = MomCfg<DIR, TX, TY, RPT, STAGES, CPS>;
   constexpr int NT = Cfg::NT, W = Cfg::W, H = Cfg::H, BW = Cfg::BW, NI = Cfg::NI, OX = Cfg::OX, OY = Cfg::OY;
   extern __shared__ unsigned char smem_raw[];
@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(TX* TY, CPS)
   double* __restrict__ s_mb = s_ma + NI;                                           // mom_flux, component b
   const int tid = threadIdx.x, lx = tid % TX, ty = tid / TX;
   const int G = gridDim.x;
-  ring_copy(va_old, va_new, nx, ny, pitch, 1, (int)blockIdx.x * NT + tid, G * NT);
-  ring_copy(vb_old, vb_new, nx, ny, pitch, 1, (int)blockIdx.x * NT + tid, G * NT);
+  pdl_trigger();
+  PdlGate gate(dep_start);
   auto issue_tile = [&](int stage, int2 xy) {
     const int j0 = 1 + xy.x * W, k0 = 1 + xy.y * H;
     ring.issue(M.m, stage, j0 - OX + XOFF, k0 - OY + 1);
@@ -93,7 +93,10 @@ __global__ void __launch_bounds__(TX* TY, CPS)
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
       const int t = (int)blockIdx.x + s * G;
-      if (t < ntiles) issue_tile(s, __ldg(order + t));
+      if (t < ntiles) {
+        gate.need(t);
+        issue_tile(s, __ldg(order + t));
+      }
     }
   }
   // the sweep axis in box / plane coordinates: moving one node along the sweep
@@ -105,6 +108,7 @@ __global__ void __launch_bounds__(TX* TY, CPS)
   int it = 0;
   for (int t = blockIdx.x; t < ntiles; t += G, ++it, cur = nxt, iss = iss_nxt) {
     const int stage = it % STAGES;
+    gate.need(t + (STAGES - 1) * G);
     if (tid == 0) {
       const int tn = t + (STAGES - 1) * G;
       if (tn < ntiles) issue_tile((stage + STAGES - 1) % STAGES, iss);
@@ -226,6 +230,10 @@ __global__ void __launch_bounds__(TX* TY, CPS)
     }
     __syncthreads();  // stage and planes are free again
   }
+  // the halo ring of the old buffers (what the preceding halo exchange / reflective boundary delivered) moves to the new ones
+  gate.finish();
+  ring_copy(va_old, va_new, nx, ny, pitch, 1, (int)blockIdx.x * NT + tid, G * NT);
+  ring_copy(vb_old, vb_new, nx, ny, pitch, 1, (int)blockIdx.x * NT + tid, G * NT);
 }
 
 template <int DIR, int MS, int TX, int TY, int RPT, int STAGES, int CPS>
@@ -242,8 +250,10 @@ static void launch_mom(const Grid& g, const MomMaps& M, const double* va_old, do
   const int ntiles = ntx * nty;
   const int cap = sm_count() * CPS;
   const int ctas = ntiles < cap ? ntiles : cap;
-  advec_mom_tma_kernel<DIR, MS, TX, TY, RPT, STAGES, CPS><<<ctas, Cfg::NT, Cfg::SMEM, stream()>>>(
-      M, va_old, va_new, vb_old, vb_new, celld, g.nx, g.ny, g.pitch, ntx, ntiles, tile_order(ntx, nty, Cfg::W));
+  const TileOrder ord = tile_order_split(ntx, nty, Cfg::W, Cfg::H, Cfg::OX, Cfg::BW - Cfg::OX - Cfg::W, Cfg::OY,
+                                         Cfg::BH - Cfg::OY - Cfg::H, g.nx, g.ny);
+  launch_pdl(advec_mom_tma_kernel<DIR, MS, TX, TY, RPT, STAGES, CPS>, dim3(ctas), dim3(Cfg::NT), Cfg::SMEM, stream(), M, va_old,
+             va_new, vb_old, vb_new, celld, g.nx, g.ny, g.pitch, ntx, ntiles, ord.table, dep_start_for(ord));
 }
 
 // ====================================================================================================================
@@ -278,7 +288,7 @@ __global__ void __launch_bounds__(TX* TY, CPS)
     advec_cell_tma_kernel(const __grid_constant__ CellMaps M, const double* __restrict__ d_old, double* __restrict__ d_new,
                           const double* __restrict__ e_old, double* __restrict__ e_new,
                           double* __restrict__ mass_flux, const double* __restrict__ vertexd, int nx, int ny, int pitch,
-                          int ntx, int nty, const int2* __restrict__ order) {
+                          int ntx, int nty, const int2* __restrict__ order, int dep_start) {
   using Cfg = CellCfg<DIR, TX, TY, RPT, STAGES, CPS>;
   constexpr int NT = Cfg::NT, W = Cfg::W, H = Cfg::H, BW = Cfg::BW, NI = Cfg::NI, OX = Cfg::OX, OY = Cfg::OY;
   constexpr int NS = DIR == 1 ? W : H;             // cells of a tile along the sweep
@@ -293,8 +303,8 @@ __global__ void __launch_bounds__(TX* TY, CPS)
   const int tid = threadIdx.x, lx = tid % TX, ty = tid / TX;
   const int G = gridDim.x;
   const int ntiles = ntx * nty;
-  ring_copy(d_old, d_new, nx, ny, pitch, 0, (int)blockIdx.x * NT + tid, G * NT);
-  ring_copy(e_old, e_new, nx, ny, pitch, 0, (int)blockIdx.x * NT + tid, G * NT);
+  pdl_trigger();
+  PdlGate gate(dep_start);
   auto issue_tile = [&](int stage, int2 xy) {
     const int j0 = 1 + xy.x * W, k0 = 1 + xy.y * H;
     ring.issue(M.m, stage, j0 - OX + XOFF, k0 - OY + 1);
@@ -303,7 +313,10 @@ __global__ void __launch_bounds__(TX* TY, CPS)
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
       const int t = (int)blockIdx.x + s * G;
-      if (t < ntiles) issue_tile(s, __ldg(order + t));
+      if (t < ntiles) {
+        gate.need(t);
+        issue_tile(s, __ldg(order + t));
+      }
     }
   }
   constexpr int SB = DIR == 1 ? 1 : BW;  // box stride along the sweep
@@ -315,6 +328,7 @@ __global__ void __launch_bounds__(TX* TY, CPS)
   int it = 0;
   for (int t = blockIdx.x; t < ntiles; t += G, ++it, cur = nxt, iss = iss_nxt) {
     const int stage = it % STAGES;
+    gate.need(t + (STAGES - 1) * G);
     if (tid == 0) {
       const int tn = t + (STAGES - 1) * G;
       if (tn < ntiles) issue_tile((stage + STAGES - 1) % STAGES, iss);
@@ -412,6 +426,10 @@ __global__ void __launch_bounds__(TX* TY, CPS)
     }
     __syncthreads();  // stage and planes are free again
   }
+  // the halo ring of the old buffers (what the preceding halo exchange / reflective boundary delivered) moves to the new ones
+  gate.finish();
+  ring_copy(d_old, d_new, nx, ny, pitch, 0, (int)blockIdx.x * NT + tid, G * NT);
+  ring_copy(e_old, e_new, nx, ny, pitch, 0, (int)blockIdx.x * NT + tid, G * NT);
 }
 
 template <int DIR, int SWEEP, int TX, int TY, int RPT, int STAGES, int CPS>
@@ -428,8 +446,10 @@ static void launch_cell(const Grid& g, const CellMaps& M, const double* d_old, d
   const int ntiles = ntx * nty;
   const int cap = sm_count() * CPS;
   const int ctas = ntiles < cap ? ntiles : cap;
-  advec_cell_tma_kernel<DIR, SWEEP, TX, TY, RPT, STAGES, CPS><<<ctas, Cfg::NT, Cfg::SMEM, stream()>>>(
-      M, d_old, d_new, e_old, e_new, mass_flux, vertexd, g.nx, g.ny, g.pitch, ntx, nty, tile_order(ntx, nty, Cfg::W));
+  const TileOrder ord = tile_order_split(ntx, nty, Cfg::W, Cfg::H, Cfg::OX, Cfg::BW - Cfg::OX - Cfg::W, Cfg::OY,
+                                         Cfg::BH - Cfg::OY - Cfg::H, g.nx, g.ny);
+  launch_pdl(advec_cell_tma_kernel<DIR, SWEEP, TX, TY, RPT, STAGES, CPS>, dim3(ctas), dim3(Cfg::NT), Cfg::SMEM, stream(), M, d_old,
+             d_new, e_old, e_new, mass_flux, vertexd, g.nx, g.ny, g.pitch, ntx, nty, ord.table, dep_start_for(ord));
 }
 
 void run_advec_cell_tma(const Grid& g, int dir, int sweep, double* vertexdx, double* vertexdy, double* volume,

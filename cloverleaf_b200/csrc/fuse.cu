@@ -28,6 +28,8 @@
 
 namespace clv {
 
+// from lagrange.cu
+void set_dt_result_seq(double s);
 // from runtime.cu
 bool tma_enabled();
 int sm_count();
@@ -58,7 +60,7 @@ __global__ void __launch_bounds__(BX* BY)
                     double* __restrict__ pressure, double* __restrict__ viscosity,
                     double* __restrict__ soundspeed, const double* __restrict__ xvel0,
                     const double* __restrict__ yvel0, double* __restrict__ partials, unsigned int* ticket,
-                    double* __restrict__ out) {
+                    double* __restrict__ out, ReduceTail RT) {
   double m[1] = {P.g_big};
   CLV_PTILES_BEGIN(r, 1)
     const size_t c = idx2(pitch, j, k);
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(BX* BY)
       }
     }
   CLV_PTILES_END
-  block_reduce_publish<1, true>(m, partials, ticket, out, P.g_big);
+  block_reduce_publish<1, true>(m, partials, ticket, out, P.g_big, RT);
 }
 
 // ---- T with TMA tile staging (tma.cuh): persistent CTAs of 32x8 threads, one cell per thread, the seven input
@@ -132,11 +134,13 @@ __global__ void __launch_bounds__(BX* BY, TT_CPS)
                         const double* __restrict__ energy0, double* __restrict__ pressure,
                         double* __restrict__ viscosity, double* __restrict__ soundspeed, double* __restrict__ partials,
                         unsigned int* ticket, double* __restrict__ out, int nx, int ny, int pitch, int ntx, int ntiles,
-                        const int2* __restrict__ order) {
+                        const int2* __restrict__ order, int dep_start, ReduceTail RT) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = align128(smem_raw);
   TimestepRing ring;
   ring.init(smem);
+  pdl_trigger();
+  PdlGate gate(dep_start);
   const int lx = threadIdx.x, ly = threadIdx.y;
   const bool leader = (lx == 0 && ly == 0);
   const int G = gridDim.x;
@@ -149,7 +153,10 @@ __global__ void __launch_bounds__(BX* BY, TT_CPS)
 #pragma unroll
     for (int s = 0; s < TT_STAGES - 1; ++s) {
       const int t = (int)blockIdx.x + s * G;
-      if (t < ntiles) issue_tile(s, __ldg(order + t));
+      if (t < ntiles) {
+        gate.need(t);
+        issue_tile(s, __ldg(order + t));
+      }
     }
   }
   // tile coordinates: host-built order table (tile_order, tma.cuh), fetched one iteration before they are needed
@@ -158,6 +165,7 @@ __global__ void __launch_bounds__(BX* BY, TT_CPS)
   int it = 0;
   for (int t = blockIdx.x; t < ntiles; t += G, ++it, cur = nxt, iss = iss_nxt) {
     const int stage = it % TT_STAGES;
+    gate.need(t + (TT_STAGES - 1) * G);  // rim tiles (and their loads, issued STAGES-1 tiles ahead) wait for the halo kernel
     if (leader) {
       const int tn = t + (TT_STAGES - 1) * G;
       if (tn < ntiles) issue_tile((stage + TT_STAGES - 1) % TT_STAGES, iss);
@@ -216,7 +224,8 @@ __global__ void __launch_bounds__(BX* BY, TT_CPS)
       }
     }
   }
-  block_reduce_publish<1, true>(m, partials, ticket, out, P.g_big);
+  gate.finish();
+  block_reduce_publish<1, true>(m, partials, ticket, out, P.g_big, RT);
 }
 
 // ================================================================================================
@@ -284,11 +293,13 @@ template <bool WRITE_SS>
 __global__ void __launch_bounds__(BX* BY, PT_CPS)
     pdv_predict_eos_tma_kernel(const __grid_constant__ PredictMaps M, double dt, double* __restrict__ pressure,
                                double* __restrict__ soundspeed, int nx, int ny, int pitch, int ntx, int ntiles,
-                        const int2* __restrict__ order) {
+                        const int2* __restrict__ order, int dep_start) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = align128(smem_raw);
   PredictRing ring;
   ring.init(smem);
+  pdl_trigger();
+  PdlGate gate(dep_start);
   const int lx = threadIdx.x, ly = threadIdx.y;
   const bool leader = (lx == 0 && ly == 0);
   const int G = gridDim.x;
@@ -300,7 +311,10 @@ __global__ void __launch_bounds__(BX* BY, PT_CPS)
 #pragma unroll
     for (int s = 0; s < PT_STAGES - 1; ++s) {
       const int t = (int)blockIdx.x + s * G;
-      if (t < ntiles) issue_tile(s, __ldg(order + t));
+      if (t < ntiles) {
+        gate.need(t);
+        issue_tile(s, __ldg(order + t));
+      }
     }
   }
   // tile coordinates: host-built order table (tile_order, tma.cuh), fetched one iteration before they are needed
@@ -309,6 +323,7 @@ __global__ void __launch_bounds__(BX* BY, PT_CPS)
   int it = 0;
   for (int t = blockIdx.x; t < ntiles; t += G, ++it, cur = nxt, iss = iss_nxt) {
     const int stage = it % PT_STAGES;
+    gate.need(t + (PT_STAGES - 1) * G);
     if (leader) {
       const int tn = t + (PT_STAGES - 1) * G;
       if (tn < ntiles) issue_tile((stage + PT_STAGES - 1) % PT_STAGES, iss);
@@ -350,6 +365,7 @@ __global__ void __launch_bounds__(BX* BY, PT_CPS)
       if (WRITE_SS) soundspeed[c] = ss;
     }
   }
+  gate.finish();
 }
 
 // ================================================================================================
@@ -486,13 +502,15 @@ struct CorrectCfg {
 template <int W, int RPT, int STAGES, int CPS>
 __global__ void __launch_bounds__(W* LT_H / RPT, CPS)
     lagrange_correct_tma_kernel(const __grid_constant__ CorrectMaps M, CorrectOut O, int nx, int ny, int pitch,
-                                double dt, int ntx, int ntiles, const int2* __restrict__ order) {
+                                double dt, int ntx, int ntiles, const int2* __restrict__ order, int dep_start) {
   using Cfg = CorrectCfg<W, RPT, STAGES, CPS>;
   constexpr int NT = Cfg::NT, VPT = Cfg::VPT, NVERT = Cfg::NVERT, ROWS = LT_H / RPT, LT_W = W, LT_BW = Cfg::BW, LT_VW = Cfg::VW;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = align128(smem_raw);
   typename Cfg::Ring ring;
   ring.init(smem);
+  pdl_trigger();
+  PdlGate gate(dep_start);
   double* __restrict__ su1 = reinterpret_cast<double*>(smem + Cfg::Ring::BYTES);
   double* __restrict__ sv1 = su1 + NVERT;
   const int tid = threadIdx.x, lx = tid % LT_W, ty = tid / LT_W;
@@ -507,7 +525,10 @@ __global__ void __launch_bounds__(W* LT_H / RPT, CPS)
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
       const int t = (int)blockIdx.x + s * G;
-      if (t < ntiles) issue_tile(s, __ldg(order + t));
+      if (t < ntiles) {
+        gate.need(t);
+        issue_tile(s, __ldg(order + t));
+      }
     }
   }
   // tile coordinates: host-built order table (tile_order, tma.cuh), fetched one iteration before they are needed
@@ -516,6 +537,7 @@ __global__ void __launch_bounds__(W* LT_H / RPT, CPS)
   int it = 0;
   for (int t = blockIdx.x; t < ntiles; t += G, ++it, cur = nxt, iss = iss_nxt) {
     const int stage = it % STAGES;
+    gate.need(t + (STAGES - 1) * G);
     if (tid == 0) {
       const int tn = t + (STAGES - 1) * G;  // its stage was released by the barrier that ended iteration it-1
       if (tn < ntiles) issue_tile((stage + STAGES - 1) % STAGES, iss);
@@ -617,6 +639,7 @@ __global__ void __launch_bounds__(W* LT_H / RPT, CPS)
     }
     __syncthreads();  // stage and su1/sv1 are free again
   }
+  gate.finish();
 }
 
 template <int W, int RPT, int STAGES, int CPS>
@@ -637,8 +660,9 @@ static void launch_correct_tma(const CorrectArgs& A, const Grid& g, double dt) {
   const int ntiles = ntx * nty;
   const int cap = sm_count() * CPS;
   const int ctas = ntiles < cap ? ntiles : cap;
-  lagrange_correct_tma_kernel<W, RPT, STAGES, CPS><<<ctas, Cfg::NT, Cfg::SMEM, stream()>>>(M, O, g.nx, g.ny, g.pitch, dt, ntx,
-                                                                                       ntiles, tile_order(ntx, nty, LT_W));
+  const TileOrder ord = tile_order_split(ntx, nty, LT_W, LT_H, LT_OX, Cfg::BW - LT_OX - LT_W, 1, LT_BH - 1 - LT_H, g.nx, g.ny);
+  launch_pdl(lagrange_correct_tma_kernel<W, RPT, STAGES, CPS>, dim3(ctas), dim3(Cfg::NT), Cfg::SMEM, stream(), M, O, g.nx, g.ny,
+             g.pitch, dt, ntx, ntiles, ord.table, dep_start_for(ord));
 }
 
 // single-call host launchers (lagrange.cu, advec.cu)
@@ -785,6 +809,8 @@ static size_t fuse_timestep(const Op* q, size_t n, size_t i) {
     const double* yv = dev(g, yvel0, VERTEX, IN);
     const DtParams P{dt.sv[0], dt.sv[1], dt.sv[2], dt.sv[3], dt.sv[4], dt.sv[5]};
     const Range r = make_range(1, g.nx, 1, g.ny);
+    const ReduceTail RT = next_reduce_tail(0);
+    set_dt_result_seq(RT.seq);
     if (!g_ctas_per_sm_timestep[0]) {
       CLV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_ctas_per_sm_timestep[0], timestep_kernel<true>,
                                                              BX * BY, 0));
@@ -805,16 +831,17 @@ static size_t fuse_timestep(const Op* q, size_t n, size_t i) {
       const int ctas = ntiles < cap ? ntiles : cap;
       double* part = partials((size_t)ctas);
       LaunchScope ls("timestep_tma");
-      timestep_tma_kernel<true><<<ctas, dim3(BX, BY), TT_SMEM, stream()>>>(M, P, cdx, cdy, d0, e0, p, qv, ss, part, ticket(),
-                                                                          host_scalars(), g.nx, g.ny, g.pitch, ntx, ntiles,
-                                                                          tile_order(ntx, nty, TT_W));
+      const TileOrder ord = tile_order_split(ntx, nty, TT_W, TT_H, 2, TT_BW - 2 - TT_W, 1, TT_BH - 1 - TT_H, g.nx, g.ny);
+      launch_pdl(timestep_tma_kernel<true>, dim3(ctas), dim3(BX, BY), TT_SMEM, stream(), M, P, cdx, cdy, d0, e0, p, qv, ss, part,
+                 ticket(), host_scalars(), g.nx, g.ny, g.pitch, ntx, ntiles, ord.table, dep_start_for(ord), RT);
     } else {
     const dim3 grid = persistent_grid(r, 1, g_ctas_per_sm_timestep[0]);
     double* part = partials((size_t)grid.x * grid.y);
     LaunchScope ls("timestep_fused");
     timestep_kernel<true><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, P, xa, ya, cdx, cdy, vol, d0, e0, p, qv, ss,
-                                                               xv, yv, part, ticket(), host_scalars());
+                                                               xv, yv, part, ticket(), host_scalars(), RT);
     }
+    note_fused_allreduce(0, 1, true, RT.all != nullptr);
   }
   if (ex2 || uh2) {
     // Nothing reads the viscosity halo before accelerate: its exchange + reflective boundary go to the side stream
@@ -877,12 +904,14 @@ static size_t fuse_predict(const Op* q, size_t n, size_t i) {
       const int cap = sm_count() * PT_CPS;
       const int ctas = ntiles < cap ? ntiles : cap;
       LaunchScope ls("pdv_predict_tma");
+      const TileOrder ord = tile_order_split(ntx, nty, PT_W, PT_H, 0, PT_BW - PT_W, 0, PT_BH - PT_H, g.nx, g.ny);
+      const int dep = dep_start_for(ord);
       if (write_ss)
-        pdv_predict_eos_tma_kernel<true><<<ctas, dim3(BX, BY), PT_SMEM, stream()>>>(M, pv.sv[0], p, ss, g.nx, g.ny, g.pitch, ntx, ntiles,
-                                                                                    tile_order(ntx, nty, PT_W));
+        launch_pdl(pdv_predict_eos_tma_kernel<true>, dim3(ctas), dim3(BX, BY), PT_SMEM, stream(), M, pv.sv[0], p, ss, g.nx, g.ny,
+                   g.pitch, ntx, ntiles, ord.table, dep);
       else
-        pdv_predict_eos_tma_kernel<false><<<ctas, dim3(BX, BY), PT_SMEM, stream()>>>(M, pv.sv[0], p, ss, g.nx, g.ny, g.pitch, ntx, ntiles,
-                                                                                     tile_order(ntx, nty, PT_W));
+        launch_pdl(pdv_predict_eos_tma_kernel<false>, dim3(ctas), dim3(BX, BY), PT_SMEM, stream(), M, pv.sv[0], p, ss, g.nx, g.ny,
+                   g.pitch, ntx, ntiles, ord.table, dep);
     } else {
     const Range r = make_range(1, g.nx, 1, g.ny);
     const dim3 grid = grid_for(r, NR_PRED);

@@ -9,6 +9,7 @@
 
 #include "clover_b200.h"
 #include "common.cuh"
+#include "lagrange.cuh"
 
 namespace clv {
 
@@ -19,6 +20,7 @@ int chunk_ny();
 const int* chunk_neighbours();
 double* chunk_field_host(int f);
 void count_copy(long long h2d, long long d2h);
+int sm_count();
 
 // Field geometry by id (data.f90:51-66; types as in clover.f90:690-880 / update_halo_kernel_c.c):
 // x_inc,y_inc = extra vertices; m = 0 for cell-centred data, 1 otherwise; sx,sy = sign applied when
@@ -95,6 +97,8 @@ __device__ __forceinline__ void update_halo_item(const FieldDesc& F, int nx, int
 __global__ void __launch_bounds__(256)
     update_halo_kernel(FieldTable T, int nx, int ny, int pitch, int depth, int ext_left, int ext_right,
                        int ext_bottom, int ext_top) {
+  pdl_wait();     // the kernel that produced the interior cells has completed
+  pdl_trigger();  // the next compute kernel may start its interior tiles (common.cuh: PDL)
   update_halo_item(T.f[blockIdx.y], nx, ny, pitch, depth, ext_left, ext_right, ext_bottom, ext_top,
                    (int)(blockIdx.x * blockDim.x + threadIdx.x));
 }
@@ -366,8 +370,8 @@ __global__ void generate_chunk_kernel(States S, int nx, int ny, int pitch, const
 //   get:     unpack;  then a grid barrier and the reflective boundary of the external faces (update_halo_kernel).
 // Two slots per face/corner, used alternately: a peer can only start writing exchange n+2 after it has received my
 // exchange n+1, which I sent after unpacking n (stream order), so slot n&1 is free again by then.
-constexpr int P2P_MAX_RANKS = 64;
-constexpr int AR_OFF = 1024, AR_SLOT = 128;  // all-reduce mailboxes: [parity][sender rank] x {8 values, sequence number}
+constexpr int P2P_MAX_RANKS = RT_MAX_RANKS;
+constexpr int AR_OFF = RT_OFF, AR_SLOT = RT_SLOT;  // all-reduce mailboxes: [parity][sender rank] x {8 values, sequence number}
 constexpr int CORNER_SLOT = 512;  // 15 fields x 2x2 doubles
 constexpr int P2P_HEADER = AR_OFF + 2 * P2P_MAX_RANKS * AR_SLOT;  // flags at face*64, tickets at 256, mailboxes at 1024
 struct PeerInfo {  // what a rank publishes about its block
@@ -389,13 +393,21 @@ struct P2P {
   unsigned long long corner_off = 0;
   int diag[4] = {-1, -1, -1, -1};         // rank of the diagonal neighbour: 0 bottom-left, 1 bottom-right, 2 top-left, 3 top-right
   unsigned long long diag_corner_off[4] = {};
-  unsigned int gen = 0, gen_bc = 0;  // exchange launches so far / of those, the ones that also did the boundary
+  unsigned int gen = 0;              // exchange launches so far = sequence number of the current one
+  unsigned int arrive_total = 0, barrier_total = 0;  // running targets of the two monotonic CTA tickets in my header
   unsigned char* all[P2P_MAX_RANKS] = {};  // every rank's block (mine included)
   unsigned char** d_all = nullptr;         // the same table on the device
   unsigned long long ar_seq = 0;
   long long bytes_sent = 0;                       // through peer memory
   long long nccl_bytes = 0, nccl_exchanges = 0;  // through the ncclSend/ncclRecv transport
 } PP;
+
+// what the last reduction kernel left in pinned memory (see answer_from_fused below)
+struct FusedAllreduce {
+  bool valid = false;
+  int base = 0, n = 0;
+  bool is_min = false;
+} FA;
 
 struct XArgs {
   int nface;                         // faces that have a neighbour
@@ -476,24 +488,44 @@ __device__ __forceinline__ void exchange_copy(const FieldTable& T, int nx, int n
     else        A.cbuf[z][f * per_corner + t] = F.p[idx2(pitch, j, k)];
   }
 }
-// grid-wide barrier (the grid is launched cooperatively: all CTAs are resident)
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+// Grid-wide barrier.  All CTAs of the exchange kernel are resident: it is launched into an otherwise idle stream
+// position (the kernels before it never wait for it, and a dependent kernel can only start once every CTA of this
+// one has started -- common.cuh: PDL), with at most one CTA per SM.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target, unsigned long long timeout_ns,
+                                             double* err, int rank) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(counter, 1u);
-    while (*(volatile unsigned int*)counter < target) {
+    unsigned long long t0 = 0;
+    unsigned int polls = 0;
+    // signed distance: the tickets wrap after 2^32 CTA arrivals
+    while ((int)(*(volatile unsigned int*)counter - target) < 0) {
+      if ((++polls & 1023u) == 0) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > timeout_ns) {
+          err[1] = (double)rank; err[2] = -1.0; err[3] = (double)target; err[4] = (double)*(volatile unsigned int*)counter;
+          __threadfence_system();
+          err[0] = 2.0;
+          __threadfence_system();
+          __trap();
+        }
+      }
     }
     __threadfence();
   }
   __syncthreads();
 }
 
-// `counters`: monotonically increasing tickets in my header; `gen` = number of exchanges so far (= the sequence
-// number every rank uses for this exchange), `gen_bc` = the ones among them that also did the boundary.
+// `counters`: monotonic tickets in my header; arrive_target / barrier_target = their values once every CTA of this
+// launch has arrived.  A.seq = number of exchanges so far = the sequence number every rank uses for this exchange.
 __global__ void __launch_bounds__(256)
     halo_exchange_kernel(FieldTable T, int nx, int ny, int pitch, int depth, XArgs A, unsigned int* counters,
-                         unsigned int gen, unsigned int gen_bc, int4 ext) {
+                         unsigned int arrive_target, unsigned int barrier_target, int4 ext, unsigned long long timeout_ns,
+                         double* err, int rank) {
+  pdl_wait();     // the kernel that produced the strips has completed
+  pdl_trigger();  // the next compute kernel may start: its interior tiles need none of what follows (common.cuh: PDL)
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
   if (A.nflag > 0) {
     exchange_copy<false>(T, nx, ny, pitch, depth, A, gtid, gsize);
@@ -501,17 +533,12 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence_system();
-      if (atomicAdd(counters + 0, 1u) + 1 == gen * gridDim.x) {
+      if (atomicAdd(counters + 0, 1u) + 1 == arrive_target) {
         __threadfence_system();
         for (int z = 0; z < A.nflag; ++z)
           asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.flag_out[z]), "l"(A.seq) : "memory");
       }
-      for (int z = 0; z < A.nflag; ++z) {
-        unsigned long long v;
-        do {
-          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(A.flag_in[z]) : "memory");
-        } while (v < A.seq);
-      }
+      for (int z = 0; z < A.nflag; ++z) spin_until_ge(A.flag_in[z], A.seq, timeout_ns, err, 1, rank, z);
     }
     __syncthreads();
     exchange_copy<true>(T, nx, ny, pitch, depth, A, gtid, gsize);
@@ -519,7 +546,7 @@ __global__ void __launch_bounds__(256)
   // the reflective boundary of the external faces (update_halo_kernel_c.c) in the same launch: its corner cells
   // mirror halo cells that the exchange has just delivered, hence the barrier
   if (ext.x | ext.y | ext.z | ext.w) {
-    grid_barrier(counters + 3, gen_bc * gridDim.x);
+    grid_barrier(counters + 3, barrier_target, timeout_ns, err, rank);
     const int ring = 2 * depth * (nx + 1 + 2 * depth) + 2 * depth * (ny + 1);
     for (int i = gtid; i < ring * T.n; i += gsize)
       update_halo_item(T.f[i / ring], nx, ny, pitch, depth, ext.x, ext.y, ext.z, ext.w, i % ring);
@@ -601,6 +628,15 @@ static bool p2p_setup(const Grid& g) {
   return PP.on;
 }
 
+void fill_reduce_tail_ranks(ReduceTail& t) {
+  if (!PP.on || N.nranks <= 1) return;
+  t.all = PP.d_all;
+  t.nranks = N.nranks;
+  t.rank = N.rank;
+  t.ar_seq = ++PP.ar_seq;
+}
+void note_fused_allreduce(int base, int n, bool is_min, bool across_ranks);
+
 static void p2p_release() {
   for (int r = 0; r < P2P_MAX_RANKS; ++r)
     if (PP.all[r] && PP.all[r] != PP.mine) cudaIpcCloseMemHandle(PP.all[r]);
@@ -615,7 +651,7 @@ static void p2p_release() {
 // 3641-3657 MPI_ALLREDUCE(MIN); clover_sum: :3621-3639 MPI_REDUCE(SUM) to rank 0).  `in`/`out` are pinned, device-visible host memory.
 __global__ void __launch_bounds__(P2P_MAX_RANKS)
     p2p_allreduce_kernel(unsigned char** all, int nranks, int rank, const double* in, double* out, int n, int is_min,
-                         unsigned long long seq) {
+                         unsigned long long seq, unsigned long long timeout_ns, double* err) {
   __shared__ double v[P2P_MAX_RANKS][8];
   const int r = threadIdx.x;
   const size_t box = AR_OFF + (size_t)(seq & 1) * P2P_MAX_RANKS * AR_SLOT;
@@ -625,10 +661,7 @@ __global__ void __launch_bounds__(P2P_MAX_RANKS)
     __threadfence_system();
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst + 8), "l"(seq) : "memory");
     const double* src = reinterpret_cast<const double*>(all[rank] + box + (size_t)r * AR_SLOT);
-    unsigned long long s;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(s) : "l"(src + 8) : "memory");
-    } while (s < seq);
+    spin_until_ge(reinterpret_cast<const unsigned long long*>(src + 8), seq, timeout_ns, err, 3, rank, r);
     for (int i = 0; i < n; ++i) v[r][i] = __ldcg(src + i);
   }
   __syncthreads();
@@ -642,7 +675,7 @@ __global__ void __launch_bounds__(P2P_MAX_RANKS)
   }
 }
 
-// the whole exchange (both phases) through peer memory: one cooperative launch
+// the whole exchange (both phases) + the reflective boundary through peer memory: one launch
 static void p2p_exchange(const Grid& g, const HaloArgs& h, const HaloArgs* bc) {
   const int* nb = chunk_neighbours();
   const FieldTable T = [&] {
@@ -698,26 +731,34 @@ static void p2p_exchange(const Grid& g, const HaloArgs& h, const HaloArgs* bc) {
       PP.bytes_sent += (long long)h.depth * ((A.face[i] < 2 ? g.ny + kFieldGeom[f].y_inc : g.nx + kFieldGeom[f].x_inc)) * 8;
     PP.bytes_sent += (long long)A.ncorner * h.depth * h.depth * 8;
   }
-  static int ctas = 0;
-  if (!ctas) {
-    int per_sm = 0;
-    CLV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, halo_exchange_kernel, 256, 0));
-    if (per_sm < 1) fatal("halo_exchange_kernel cannot be resident");
-    int dev_id = 0, sms = 0;
-    CLV_CUDA(cudaGetDevice(&dev_id));
-    CLV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_id));
-    ctas = sms;  // one CTA per SM is enough for <= 0.5 MB of strips and keeps the grid barrier cheap
-  }
-  unsigned int* counters = (unsigned int*)(PP.mine + 256);
-  int nx = g.nx, ny = g.ny, pitch = g.pitch, depth = h.depth;
-  FieldTable Tc = T;
+  // grid: ~4 strip elements per thread, at most one CTA per SM (all resident: the kernel has a grid barrier)
+  long long elements = 0;
+  for (int i = 0; i < A.nface; ++i) elements += (long long)T.n * h.depth * ((A.face[i] < 2 ? g.ny : g.nx) + 1 + 2 * h.depth);
   int4 ext = make_int4(0, 0, 0, 0);
   if (bc) ext = make_int4(bc->ext[0], bc->ext[1], bc->ext[2], bc->ext[3]);
-  if (ext.x | ext.y | ext.z | ext.w) ++PP.gen_bc;
-  unsigned int gen_bc = PP.gen_bc;
-  void* args[] = {&Tc, &nx, &ny, &pitch, &depth, &A, &counters, (void*)&gen, &gen_bc, &ext};
-  LaunchScope ls("halo_exchange_p2p");
-  CLV_CUDA(cudaLaunchCooperativeKernel((void*)halo_exchange_kernel, dim3((unsigned)ctas), dim3(256), args, 0, stream()));
+  const bool reflect = (ext.x | ext.y | ext.z | ext.w) != 0;
+  if (reflect) {
+    const long long ring = (long long)T.n * (2 * h.depth * (g.nx + 1 + 2 * h.depth) + 2 * h.depth * (g.ny + 1));
+    if (ring > elements) elements = ring;
+  }
+  static int max_ctas = 0;
+  if (!max_ctas) {
+    max_ctas = sm_count();
+    if (const char* e = getenv("CLOVER_B200_XCTAS")) max_ctas = atoi(e) > 0 ? atoi(e) : max_ctas;
+    if (max_ctas > sm_count()) max_ctas = sm_count();
+  }
+  int ctas = (int)((elements + 256 * 4 - 1) / (256 * 4));
+  if (ctas < 1) ctas = 1;
+  if (ctas > max_ctas) ctas = max_ctas;
+  unsigned int* counters = (unsigned int*)(PP.mine + 256);
+  PP.arrive_total += (A.nflag > 0) ? (unsigned)ctas : 0u;
+  if (reflect) PP.barrier_total += (unsigned)ctas;
+  {
+    LaunchScope ls("halo_exchange_p2p");
+    launch_pdl(halo_exchange_kernel, dim3((unsigned)ctas), dim3(256), 0, stream(), T, g.nx, g.ny, g.pitch, h.depth, A, counters,
+               PP.arrive_total, PP.barrier_total, ext, spin_timeout_ns(), device_error_record(), N.rank);
+  }
+  note_halo_launch();
 }
 
 // ---- update_halo and the NCCL exchange on their own (host side) ---------------------------------------
@@ -737,6 +778,13 @@ static FieldTable field_table(const Grid& g, const HaloArgs& h, int depth, int e
   return T;
 }
 
+void note_fused_allreduce(int base, int n, bool is_min, bool across_ranks) {
+  FA.valid = across_ranks;
+  FA.base = base;
+  FA.n = n;
+  FA.is_min = is_min;
+}
+
 void run_update_halo(const Grid& g, const HaloArgs& h) {
   const FieldTable T = field_table(g, h, h.depth, 0);
   if (T.n > 0 && (h.ext[0] || h.ext[1] || h.ext[2] || h.ext[3])) {
@@ -752,9 +800,12 @@ void run_update_halo(const Grid& g, const HaloArgs& h) {
     }
     const int ring = 2 * h.depth * (g.nx + 1 + 2 * h.depth) + 2 * h.depth * (g.ny + 1);
     const dim3 grid((unsigned)((ring + 255) / 256), (unsigned)T.n);
-    LaunchScope ls("update_halo");
-    update_halo_kernel<<<grid, 256, 0, stream()>>>(T, g.nx, g.ny, g.pitch, h.depth, h.ext[0], h.ext[1], h.ext[2],
-                                                   h.ext[3]);
+    {
+      LaunchScope ls("update_halo");
+      launch_pdl(update_halo_kernel, grid, dim3(256), 0, stream(), T, g.nx, g.ny, g.pitch, h.depth, h.ext[0], h.ext[1],
+                 h.ext[2], h.ext[3]);
+    }
+    note_halo_launch();
   }
 }
 
@@ -924,11 +975,37 @@ void clover_b200_exchange_(int* fields, int* depth_p) {
   submit(std::move(op));
 }
 
+// The reduction kernels (calc_dt / the fused timestep launch, field_summary) fold across ranks themselves when the
+// peer-memory transport is up (lagrange.cuh: block_reduce_publish).  What they leave in pinned memory -- this rank's
+// values at [base+32..], the all-rank result at [base..] -- is remembered here, and the clover_min / clover_sum call
+// the driver makes next (timestep.f90:90, field_summary.f90:103-107) is answered from it without a launch.
+
+static bool answer_from_fused(double* values, int n, bool is_min) {
+  if (!FA.valid || FA.is_min != is_min || FA.n != n) return false;
+  FA.valid = false;
+  const double* h = host_scalars();
+  if (is_min) {
+    // min over ranks of min(local_r, c) with a rank-uniform c (timestep.f90:86-89: dtold*dtrise, dtmax) equals
+    // min(global, value); anything else is not the call sequence this answer is valid for
+    if (!(values[0] <= h[FA.base + 32]))
+      fatal("clover_b200_min_: the value passed (%.17g) exceeds the dt_min_val calc_dt returned (%.17g)", values[0],
+            h[FA.base + 32]);
+    if (h[FA.base] < values[0]) values[0] = h[FA.base];
+    return true;
+  }
+  for (int i = 0; i < n; ++i)
+    if (values[i] != h[FA.base + 32 + i])
+      fatal("clover_b200_sum_: the values passed are not the ones field_summary_kernel_c_ returned");
+  for (int i = 0; i < n; ++i) values[i] = h[FA.base + i];
+  return true;
+}
+
 static void allreduce_host(double* values, int n, ncclRedOp_t op) {
   ensure_init();
   flush_deferred();
   if (!N.comm || N.nranks == 1) return;
   if (n > 16) fatal("allreduce of %d values (max 16)", n);
+  if (answer_from_fused(values, n, op == ncclMin)) return;
   if (n <= 8 && chunk_registered()) {
     int one = 1, nx = chunk_nx(), ny = chunk_ny();
     if (p2p_setup(grid_of_noflush(&one, &nx, &one, &ny))) {
@@ -937,7 +1014,8 @@ static void allreduce_host(double* values, int n, ncclRedOp_t op) {
       {
         LaunchScope ls("allreduce_p2p");
         p2p_allreduce_kernel<<<1, P2P_MAX_RANKS, 0, stream()>>>(PP.d_all, N.nranks, N.rank, h + 16, h + 24, n,
-                                                               op == ncclMin ? 1 : 0, ++PP.ar_seq);
+                                                               op == ncclMin ? 1 : 0, ++PP.ar_seq, spin_timeout_ns(),
+                                                               device_error_record());
       }
       CLV_CUDA(cudaStreamSynchronize(stream()));
       for (int i = 0; i < n; ++i) values[i] = h[24 + i];

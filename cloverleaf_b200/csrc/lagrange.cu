@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(BX* BY)
                    const double* __restrict__ density0, const double* __restrict__ viscosity,
                    const double* __restrict__ soundspeed, const double* __restrict__ xvel0,
                    const double* __restrict__ yvel0, double* __restrict__ partials,
-                   unsigned int* ticket, double* __restrict__ out) {
+                   unsigned int* ticket, double* __restrict__ out, ReduceTail RT) {
   double m[1] = {P.g_big};
   CLV_PTILES_BEGIN(r, NR)
     const size_t c = idx2(pitch, j, k);
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(BX* BY)
     if (bad) cell_dt = calc_dt_cell<true>(in, P, bad);
     if (active && cell_dt < m[0]) m[0] = cell_dt;
   CLV_PTILES_END
-  block_reduce_publish<1, true>(m, partials, ticket, out, P.g_big);
+  block_reduce_publish<1, true>(m, partials, ticket, out, P.g_big, RT);
 }
 
 // field_summary_kernel_c.c:66-89.  6 passes read = 48 B/cell.
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(BX* BY)
                          const double* __restrict__ density0, const double* __restrict__ energy0,
                          const double* __restrict__ pressure, const double* __restrict__ xvel0,
                          const double* __restrict__ yvel0, double* __restrict__ partials,
-                         unsigned int* ticket, double* __restrict__ out) {
+                         unsigned int* ticket, double* __restrict__ out, ReduceTail RT) {
   double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};  // vol, mass, ie, ke, press
   CLV_PTILES_BEGIN(r, NR)
     const size_t c = idx2(pitch, j, k);
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(BX* BY)
       s[4] += cell_vol * pressure[c];
     }
   CLV_PTILES_END
-  block_reduce_publish<5, false>(s, partials, ticket, out, 0.0);
+  block_reduce_publish<5, false>(s, partials, ticket, out, 0.0, RT);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -375,7 +375,10 @@ void run_viscosity(const Grid& g, double* celldx, double* celldy, double* densit
   viscosity_kernel<NR_VISC><<<grid_for(r, NR_VISC), dim3(BX, BY), 0, stream()>>>(r, g.pitch, cdx, cdy, d0, p, q, xv, yv);
 }
 
-// the result lands in host_scalars()[0] once the stream has drained
+// the result lands in host_scalars()[0]; host_scalars()[7] then shows dt_result_seq()
+double g_dt_seq = 0;
+double dt_result_seq() { return g_dt_seq; }
+void set_dt_result_seq(double s) { g_dt_seq = s; }
 void run_calc_dt(const Grid& g, const DtParams& P, double* xarea, double* yarea, double* celldx, double* celldy,
                  double* volume, double* density0, double* viscosity, double* soundspeed, double* xvel0,
                  double* yvel0) {
@@ -392,9 +395,14 @@ void run_calc_dt(const Grid& g, const DtParams& P, double* xarea, double* yarea,
   const Range r = make_range(1, g.nx, 1, g.ny);
   const dim3 grid = persistent_grid(r, NR_DT, 6);
   double* part = partials((size_t)grid.x * grid.y);
-  LaunchScope ls("calc_dt");
-  calc_dt_kernel<NR_DT><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, P, xa, ya, cdx, cdy, vol, d0, q, ss, xv, yv,
-                                                             part, ticket(), host_scalars());
+  const ReduceTail RT = next_reduce_tail(0);
+  g_dt_seq = RT.seq;
+  {
+    LaunchScope ls("calc_dt");
+    calc_dt_kernel<NR_DT><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, P, xa, ya, cdx, cdy, vol, d0, q, ss, xv, yv,
+                                                               part, ticket(), host_scalars(), RT);
+  }
+  note_fused_allreduce(0, 1, true, RT.all != nullptr);
 }
 
 void run_pdv(const Grid& g, bool predict, double dt, double* xarea, double* yarea, double* volume, double* density0,
@@ -572,8 +580,13 @@ void calc_dt_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double* g_sma
   op.run = [=] { run_calc_dt(g, P, xarea, yarea, celldx, celldy, volume, density0, viscosity, soundspeed, xvel0, yvel0); };
   submit(std::move(op));
   flush_deferred();
-  CLV_CUDA(cudaStreamSynchronize(stream()));  // the one unavoidable host-visible result per step
-  const double v = host_scalars()[0];
+  // the one unavoidable host-visible result per step: the host spins on the sequence number the reduction tail
+  // writes to pinned memory after the value (no stream synchronisation: launches that follow calc_dt in the
+  // stream, e.g. the viscosity halo exchange, keep running).  With several ranks the kernel has already folded the
+  // minimum across ranks (host_scalars()[0]); calc_dt's own contract is the LOCAL minimum ([32]); clover_b200_min_
+  // hands out the global one.
+  wait_scalars(0, dt_result_seq());
+  const double v = host_scalars()[32];
   *dt_min_val = v;
   *dtl_control = 1;  // calc_dt_kernel_c.c:159-163
   *jldt = 1;
@@ -686,17 +699,20 @@ void field_summary_kernel_c_(int* xmin, int* xmax, int* ymin, int* ymax, double*
   const dim3 grid = persistent_grid(r, NR_SUM, 6);
   double* part = partials((size_t)grid.x * grid.y * 5);
   double* out = host_scalars() + 8;
+  const ReduceTail RT = next_reduce_tail(8);
   {
     LaunchScope ls("field_summary");
     field_summary_kernel<NR_SUM><<<grid, dim3(BX, BY), 0, stream()>>>(r, g.pitch, v, d0, e0, p, x0, y0, part,
-                                                                      ticket() + 1, out);
+                                                                      ticket() + 1, out, RT);
   }
-  CLV_CUDA(cudaStreamSynchronize(stream()));
-  *vol = out[0];
-  *mass = out[1];
-  *ie = out[2];
-  *ke = out[3];
-  *press = out[4];
+  note_fused_allreduce(8, 5, false, RT.all != nullptr);
+  wait_scalars(8, RT.seq);
+  // this rank's sums (the kernel's contract); the sums over all ranks are already in out[0..4] for clover_b200_sum_
+  *vol = out[32 + 0];
+  *mass = out[32 + 1];
+  *ie = out[32 + 2];
+  *ke = out[32 + 3];
+  *press = out[32 + 4];
   finish();
 }
 

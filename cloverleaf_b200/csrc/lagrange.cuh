@@ -111,13 +111,48 @@ __device__ __forceinline__ double viscosity_cell(const ViscIn& I, bool& bad) {
 
 // ------------------------------------------------------------------------------------------------
 // Block-level reduction tails shared by calc_dt and field_summary: every block publishes its
-// partial(s), the last block to arrive (ticket) folds them in a fixed order and writes the result
-// to pinned host memory, then re-arms the ticket.
+// partial(s), the last block to arrive (ticket) folds them in a fixed order.  With several ranks
+// (ReduceTail.all != nullptr) the same block then folds ACROSS ranks over peer memory -- thread r drops this
+// rank's values + sequence number into its mailbox in rank r's block and waits for rank r's (bounded spin), thread 0
+// folds in rank order, so every rank holds bit-identical results -- which replaces clover_min / clover_sum
+// (clover.f90:3621-3657) without a launch or a host round trip of their own.  Results go to pinned host memory:
+//   out[0..N)  the (global) result    out[32..32+N)  this rank's local result    out[7]  sequence number, written
+// last (the host spins on it instead of synchronising the stream; runtime.cu: wait_scalars).
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded system-scope spin: returns once *flag >= want; after timeout_ns writes an error record
+// {code, rank, who, want, seen} to err (pinned host memory, printed by the host's CUDA error path) and traps.
+__device__ __forceinline__ void spin_until_ge(const unsigned long long* flag, unsigned long long want,
+                                              unsigned long long timeout_ns, double* err, int code, int rank, int who) {
+  unsigned long long v, t0 = 0;
+  unsigned int polls = 0;
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= want) return;
+    if ((++polls & 1023u) == 0) {
+      const unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > timeout_ns) break;
+    }
+  }
+  if (err) {
+    err[1] = (double)rank; err[2] = (double)who; err[3] = (double)want; err[4] = (double)v;
+    __threadfence_system();
+    err[0] = (double)code;
+    __threadfence_system();
+  }
+  __trap();
+}
+
 template <int N, bool IS_MIN>
 __device__ __forceinline__ void block_reduce_publish(double (&v)[N], double* __restrict__ partials,
                                                      unsigned int* ticket, double* __restrict__ out,
-                                                     double identity) {
+                                                     double identity, const ReduceTail& RT) {
   __shared__ double sm[N][BX * BY / 32];
+  __shared__ double xr[RT_MAX_RANKS][N];
   __shared__ bool last;
   const int tid = threadIdx.y * BX + threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -159,9 +194,41 @@ __device__ __forceinline__ void block_reduce_publish(double (&v)[N], double* __r
     for (int i = 0; i < N; ++i) {
       double a = sm[i][0];
       for (int w = 1; w < BX * BY / 32; ++w) a = IS_MIN ? ((sm[i][w] < a) ? sm[i][w] : a) : a + sm[i][w];
-      out[i] = a;
+      sm[i][0] = a;  // this rank's result
+      out[32 + i] = a;
     }
     *ticket = 0;
+  }
+  __syncthreads();
+  if (RT.all != nullptr) {
+    // ---- across ranks, over peer memory (mailbox [parity][sender] of RT_SLOT bytes: 8 values + sequence number)
+    const size_t box = RT_OFF + (size_t)(RT.ar_seq & 1) * RT_MAX_RANKS * RT_SLOT;
+    if (tid < RT.nranks) {
+      double* dst = reinterpret_cast<double*>(RT.all[tid] + box + (size_t)RT.rank * RT_SLOT);
+#pragma unroll
+      for (int i = 0; i < N; ++i) dst[i] = sm[i][0];
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst + 8), "l"(RT.ar_seq) : "memory");
+      const double* src = reinterpret_cast<const double*>(RT.all[RT.rank] + box + (size_t)tid * RT_SLOT);
+      spin_until_ge(reinterpret_cast<const unsigned long long*>(src + 8), RT.ar_seq, RT.timeout_ns, RT.err, 3, RT.rank, tid);
+#pragma unroll
+      for (int i = 0; i < N; ++i) xr[tid][i] = __ldcg(src + i);
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        double a = xr[0][i];
+        for (int q = 1; q < RT.nranks; ++q) a = IS_MIN ? ((xr[q][i] < a) ? xr[q][i] : a) : a + xr[q][i];
+        sm[i][0] = a;
+      }
+    }
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = sm[i][0];
+    __threadfence_system();
+    out[7] = RT.seq;
     __threadfence_system();
   }
 }

@@ -54,6 +54,7 @@ struct Runtime {
   bool resident = true;
   std::unordered_map<const void*, Entry> arrays;
   std::unordered_map<const void*, Buffer> buffers;
+  std::multimap<size_t, double*> pool;   // parked device buffers by size in doubles (see alloc_zeroed)
   std::vector<const void*> pending_out;  // non-resident mode: arrays to download in finish()
   double* h_scalars = nullptr;           // pinned + mapped
   double* d_partials = nullptr;
@@ -66,13 +67,18 @@ struct Runtime {
   bool draining = false;
   bool fuse = true;
   bool tma = true;
-  bool overlap = true;
+  bool overlap = false;  // side-stream overlap of the viscosity exchange: superseded by PDL ($CLOVER_B200_OVERLAP=1 re-enables)
   cudaStream_t side = nullptr;   // second stream: a halo exchange that nothing waits for yet (see side_begin)
   cudaStream_t cur = nullptr;    // non-null while work is being issued to the side stream
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool side_pending = false;
   int sms = 148;
   int lazy_pending = 0;   // number of entries with lazy_src set
+  bool pdl = true;        // programmatic dependent launch ($CLOVER_B200_PDL=0 disables)
+  bool split = true;      // interior tiles before the halo wait ($CLOVER_B200_SPLIT=0: wait before the first tile)
+  bool halo_noted = false;  // the last launch was an exchange / update_halo kernel
+  unsigned long long scalar_seq = 0;               // sequence number of the reduction results in h_scalars
+  unsigned long long spin_timeout_ns = 20000000000ull;  // device-side waits for other GPUs ($CLOVER_B200_SPIN_TIMEOUT_MS)
   std::map<std::string, Prof> prof;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -143,11 +149,28 @@ void download(const Entry& e, double* host) {
   }
 }
 
+// Device allocations are pooled by size: a mirror that is forgotten (clover_b200_forget_, a host address re-used with
+// another shape) parks its buffers here and the next mirror of that size takes them -- no cudaMalloc / cudaFree on
+// the path of a run that re-creates its arrays, and tensor maps encoded for a parked buffer stay valid (they depend
+// on address and shape only).  clover_b200_invalidate_ / finalize_ really free the pool.
 double* alloc_zeroed(size_t doubles) {
   double* p = nullptr;
-  CLV_CUDA(cudaMalloc(&p, doubles * sizeof(double)));
+  auto it = R.pool.find(doubles);
+  if (it != R.pool.end()) {
+    p = it->second;
+    R.pool.erase(it);
+  } else {
+    CLV_CUDA(cudaMalloc(&p, doubles * sizeof(double)));
+  }
   CLV_CUDA(cudaMemsetAsync(p, 0, doubles * sizeof(double), R.stream));
   return p;
+}
+void park(double* p, size_t doubles) {
+  if (p) R.pool.emplace(doubles, p);
+}
+void free_pool() {
+  for (auto& kv : R.pool) CLV_CUDA(cudaFree(kv.second));
+  R.pool.clear();
 }
 
 size_t doubles_for(Kind kind, int nx, int ny) {
@@ -272,11 +295,9 @@ static Entry& lookup(const Grid& g, const double* host, Kind kind, bool* fresh) 
     // same host address re-used with another shape (e.g. a work array): re-create the mirror
     materialize_dependents(host);
     drop_lazy(e);
-    CLV_CUDA(cudaStreamSynchronize(R.stream));
-    CLV_CUDA(cudaFree(e.d));
-    if (e.alt) CLV_CUDA(cudaFree(e.alt));
+    park(e.d, e.doubles);
+    park(e.alt, e.doubles);
     R.arrays.erase(it);
-    drop_tensor_maps();
   }
   Entry e;
   e.kind = kind;
@@ -402,8 +423,10 @@ void finish() {
 LaunchScope::LaunchScope(const char* n) : name(n) {
   if (R.profiling) CLV_CUDA(cudaEventRecord(R.ev0, R.stream));
 }
+
 LaunchScope::~LaunchScope() {
   R.launches++;
+  R.halo_noted = false;  // halo.cu re-notes after its scope closes; any other launch ends the "just launched" state
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) fatal("launch of %s failed: %s", name, cudaGetErrorString(e));
   if (R.profiling) {
@@ -418,6 +441,63 @@ LaunchScope::~LaunchScope() {
 }
 
 double* host_scalars() { return R.h_scalars; }
+double* device_error_record() { return R.h_scalars + 48; }
+unsigned long long spin_timeout_ns() { return R.spin_timeout_ns; }
+
+// A kernel that gave up waiting for another GPU (or for its own grid) left a record in pinned host memory before it
+// trapped; the CUDA error that follows the trap brings us here.
+void report_device_error() {
+  if (!R.h_scalars) return;
+  const volatile double* e = R.h_scalars + 48;
+  const int code = (int)e[0];
+  if (code == 0) return;
+  static const char* what[] = {"", "halo exchange: a neighbour's strips never arrived", "halo exchange: grid barrier never completed",
+                               "all-reduce: a rank's contribution never arrived"};
+  fprintf(stderr,
+          "libclover_b200: device-side time-out (%.1f s) on rank %d: %s (peer/slot %d, waiting for sequence number %.0f, "
+          "last seen %.0f).  A peer process has died or fallen out of step; aborting instead of hanging the GPU.\n",
+          (double)R.spin_timeout_ns * 1e-9, (int)e[1], (code >= 1 && code <= 3) ? what[code] : "unknown wait", (int)e[2], e[3], e[4]);
+}
+
+ReduceTail next_reduce_tail(int base) {
+  ReduceTail t;
+  t.seq = (double)(++R.scalar_seq);
+  t.all = nullptr;
+  t.nranks = 1;
+  t.rank = 0;
+  t.ar_seq = 0;
+  t.timeout_ns = R.spin_timeout_ns;
+  t.err = R.h_scalars + 48;
+  (void)base;
+  fill_reduce_tail_ranks(t);
+  return t;
+}
+
+void wait_scalars(int base, double seq) {
+  const volatile double* flag = R.h_scalars + base + 7;
+  unsigned long long spins = 0;
+  struct timeval t0;
+  gettimeofday(&t0, nullptr);
+  while (*flag != seq) {
+    if ((++spins & 0xfff) == 0) {
+      const cudaError_t q = cudaStreamQuery(R.stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady) CLV_CUDA(q);
+      if (q == cudaSuccess && *flag != seq) {  // the stream has drained and the kernel never wrote: cannot happen
+        if (*flag != seq) fatal("reduction result %d never arrived (stream idle)", base);
+      }
+      struct timeval t1;
+      gettimeofday(&t1, nullptr);
+      if (t1.tv_sec - t0.tv_sec > 60) {
+        report_device_error();
+        fatal("reduction result %d not delivered after 60 s", base);
+      }
+    }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+  __sync_synchronize();
+}
 unsigned int* ticket() { return R.d_ticket; }
 double* partials(size_t doubles) {
   if (R.partials_doubles < doubles) {
@@ -512,6 +592,47 @@ const int2* tile_order(int ntx, int nty, int tw) {
   return d;
 }
 
+namespace {
+std::map<std::tuple<int, int, int, int, int, int, int, int, int, int>, TileOrder> g_split_orders;
+}
+TileOrder tile_order_split(int ntx, int nty, int tw, int th, int lo_x, int hi_x, int lo_y, int hi_y, int nx, int ny) {
+  constexpr int BAND_COLS = 4096;
+  const int band_tiles = (ntx * tw <= BAND_COLS + 256) ? ntx : (BAND_COLS / tw > 0 ? BAND_COLS / tw : 1);
+  const auto key = std::make_tuple(ntx, nty, tw, th, lo_x, hi_x, lo_y, hi_y, nx, ny);
+  auto it = g_split_orders.find(key);
+  if (it != g_split_orders.end()) return it->second;
+  auto interior = [&](int tx, int ty) {
+    const int j0 = 1 + tx * tw, k0 = 1 + ty * th;
+    return j0 - lo_x >= 1 && j0 + tw - 1 + hi_x <= nx && k0 - lo_y >= 1 && k0 + th - 1 + hi_y <= ny;
+  };
+  std::vector<int2> h;
+  h.reserve((size_t)ntx * nty);
+  for (int pass = 0; pass < 2; ++pass) {  // 0: interior tiles, 1: rim tiles; each banded, row by row inside a band
+    for (int x0 = 0; x0 < ntx; x0 += band_tiles) {
+      const int w = (ntx - x0 < band_tiles) ? ntx - x0 : band_tiles;
+      for (int ty = 0; ty < nty; ++ty)
+        for (int tx = x0; tx < x0 + w; ++tx)
+          if (interior(tx, ty) == (pass == 0)) h.push_back(make_int2(tx, ty));
+    }
+    if (pass == 0) g_split_orders[key].n_interior = (int)h.size();
+  }
+  if ((int)h.size() != ntx * nty) fatal("tile_order_split: %zu entries for %d x %d tiles", h.size(), ntx, nty);
+  int2* d = nullptr;
+  CLV_CUDA(cudaMalloc(&d, h.size() * sizeof(int2)));
+  CLV_CUDA(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice, R.stream));
+  CLV_CUDA(cudaStreamSynchronize(R.stream));
+  TileOrder& o = g_split_orders[key];
+  o.table = d;
+  o.ntiles = ntx * nty;
+  return o;
+}
+
+// ---- programmatic dependent launch bookkeeping (common.cuh) ----------------------------------------------------
+bool pdl_enabled() { return R.pdl && !R.profiling; }
+void note_halo_launch() { R.halo_noted = true; }
+bool halo_just_launched() { return R.halo_noted; }
+int dep_start_for(const TileOrder& o) { return (halo_just_launched() && pdl_enabled() && R.split) ? o.n_interior : 0; }
+
 // used by halo.cu
 bool chunk_registered() { return C.set; }
 int chunk_nx() { return C.nx; }
@@ -550,6 +671,10 @@ void clover_b200_init_(int* device) {
   CLV_CUDA(cudaMemset(R.d_ticket, 0, 16 * sizeof(unsigned int)));
   CLV_CUDA(cudaEventCreate(&R.ev0));
   CLV_CUDA(cudaEventCreate(&R.ev1));
+  if (const char* s = getenv("CLOVER_B200_PDL")) R.pdl = (atoi(s) != 0);
+  if (const char* s = getenv("CLOVER_B200_SPIN_TIMEOUT_MS")) R.spin_timeout_ns = (unsigned long long)atoll(s) * 1000000ull;
+  memset(R.h_scalars, 0, 64 * sizeof(double));
+  if (const char* s = getenv("CLOVER_B200_SPLIT")) R.split = (atoi(s) != 0);
   if (const char* s = getenv("CLOVER_B200_FUSE")) R.fuse = (atoi(s) != 0);
   if (const char* s = getenv("CLOVER_B200_TMA")) R.tma = (atoi(s) != 0);  // A/B switch for profiling
   R.sms = p.multiProcessorCount;
@@ -570,6 +695,7 @@ void clover_b200_finalize_(void) {
   R.partials_doubles = 0;
   CLV_CUDA(cudaFree(R.d_ticket));
   CLV_CUDA(cudaFreeHost(R.h_scalars));
+  R.h_scalars = nullptr;
   CLV_CUDA(cudaEventDestroy(R.ev0));
   CLV_CUDA(cudaEventDestroy(R.ev1));
   CLV_CUDA(cudaStreamDestroy(R.stream));
@@ -600,6 +726,7 @@ void clover_b200_invalidate_(void) {
     if (kv.second.alt) CLV_CUDA(cudaFree(kv.second.alt));
   }
   R.arrays.clear();
+  free_pool();
   drop_tensor_maps();
   R.lazy_pending = 0;
   for (auto& kv : R.buffers) CLV_CUDA(cudaFree(kv.second.d));
@@ -615,11 +742,9 @@ void clover_b200_forget_(double* host) {
   if (it != R.arrays.end()) {
     materialize_dependents(host);
     drop_lazy(it->second);
-    CLV_CUDA(cudaStreamSynchronize(R.stream));
-    CLV_CUDA(cudaFree(it->second.d));
-    if (it->second.alt) CLV_CUDA(cudaFree(it->second.alt));
+    park(it->second.d, it->second.doubles);  // stream order keeps a later user of the buffer behind its last use here
+    park(it->second.alt, it->second.doubles);
     R.arrays.erase(it);
-    drop_tensor_maps();
   }
   auto ib = R.buffers.find(host);
   if (ib != R.buffers.end()) {

@@ -32,6 +32,19 @@ const CUtensorMap* tensor_map_for(const Grid& g, const double* dev_ptr, int box_
 // chunks are walked down bands of ~4096 columns, which keeps both properties (a 15360-wide chunk walked row by row
 // re-fetched its halo rows from DRAM: ncu showed 1.16x - 2.1x the compulsory reads, against 1.00x - 1.05x at 3840).
 const int2* tile_order(int ntx, int nty, int tw);
+// The same table with the tiles whose input boxes lie entirely inside the cells 1..nx x 1..ny (no halo cell, hence
+// no dependence on a preceding halo exchange / reflective boundary) in front, banded as above, followed by the rim
+// tiles; n_interior = how many there are.  Tile (tx,ty) reads the columns 1+tx*tw-lo_x .. 1+(tx+1)*tw-1+hi_x and the
+// rows 1+ty*th-lo_y .. 1+(ty+1)*th-1+hi_y.  See "programmatic dependent launch" in common.cuh.
+struct TileOrder {
+  const int2* table;
+  int ntiles;
+  int n_interior;
+};
+TileOrder tile_order_split(int ntx, int nty, int tw, int th, int lo_x, int hi_x, int lo_y, int hi_y, int nx, int ny);
+// dep_start for a compute launch: the number of interior tiles when the previous launch was a halo kernel, else 0
+// (wait before the first tile).
+int dep_start_for(const TileOrder& o);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

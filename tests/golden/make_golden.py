@@ -32,11 +32,61 @@ def shrink(deck, n):
     return deck.replace("x_cells=960", "x_cells=%d" % n).replace("y_cells=960", "y_cells=%d" % n)
 
 
-def record(name, deck, nchunks=1, end_step=None, fields=False):
+def exact_summary(d):
+    """field_summary_kernel_c.c:52-88 evaluated on the reference run's own fields with the per-cell terms formed
+    exactly as the kernel forms them (same operations, same order) but SUMMED in 80-bit pairwise arithmetic.  The
+    reference accumulates serially in fp64, which at 7680^2 / 15360^2 cells carries ~2e-10 / ~1e-9 relative
+    rounding of its own (its mass reads 28.000000005 for an exact 28); this is the sum a 1e-10 bar can be held to."""
+    import ctypes
+    import numpy as np
+    from cloverleaf_b200.driver import FIELD_SHAPES
+    info = d.chunk_info(0)
+    nx, ny = info["x_max"], info["y_max"]
+
+    def view(name):  # no copy: 15360^2 fields are 1.9 GB each
+        ex, ey = FIELD_SHAPES[name]
+        w, h = nx + 4 + ex, ny + 4 + ey
+        p = d._L.clover_driver_field(d._h, 0, name.encode())
+        return np.frombuffer((ctypes.c_double * (w * h)).from_address(p), dtype=np.float64).reshape(h, w)
+
+    VOL, RHO, EN, PR, U, V = (view(n) for n in ("volume", "density0", "energy0", "pressure", "xvel0", "yvel0"))
+    ld = np.longdouble
+    acc = dict(volume=ld(0), mass=ld(0), ie=ld(0), ke=ld(0), pressure=ld(0))
+    B = 256
+    for k0 in range(2, 2 + ny, B):  # array row index of cell k is k+1; cells 1..ny -> rows 2..ny+1
+        k1 = min(k0 + B, 2 + ny)
+        sl = (slice(k0, k1), slice(2, 2 + nx))
+        vol, rho, en, pr = VOL[sl], RHO[sl], EN[sl], PR[sl]
+        vsq = np.zeros_like(vol)
+        for kv in (0, 1):          # field_summary_kernel_c.c:74-79: kv outer, jv inner
+            for jv in (0, 1):
+                uu = U[k0 + kv:k1 + kv, 2 + jv:2 + nx + jv]
+                vv = V[k0 + kv:k1 + kv, 2 + jv:2 + nx + jv]
+                vsq = vsq + 0.25 * (uu * uu + vv * vv)
+        mass = vol * rho
+        acc["volume"] += np.sum(vol, dtype=ld)
+        acc["mass"] += np.sum(mass, dtype=ld)
+        acc["ie"] += np.sum(mass * en, dtype=ld)
+        acc["ke"] += np.sum(mass * 0.5 * vsq, dtype=ld)
+        acc["pressure"] += np.sum(vol * pr, dtype=ld)
+    out = dict(step=float(d.step), **{k: float(v) for k, v in acc.items()})
+    out["pressure"] = out["pressure"] / out["volume"]  # the driver reports press/vol (field_summary.f90:129)
+    out["density"] = out["mass"] / out["volume"]
+    out["total"] = out["ie"] + out["ke"]
+    return out
+
+
+def record(name, deck, nchunks=1, end_step=None, fields=False, exact=False):
     d = Driver(deck, REF, nchunks=nchunks, end_step=end_step)
+    ex = []
+    if exact:
+        d.start()                  # start.f90:145 has just done the initial field_summary (ideal_gas included)
+        ex.append(exact_summary(d))
     d.run()
+    if exact:
+        ex.append(exact_summary(d))  # the final field_summary ran ideal_gas on the final state
     G = dict(deck=deck, nchunks=nchunks, end_step=end_step, steps=d.step, dt=d.dts().tolist(),
-             summaries=d.summaries(),
+             summaries=d.summaries(), summaries_exact=ex,
              source="oracle/_ref/libclover_ref_c.so (reference C kernels), %s thread(s)" % os.environ["OMP_NUM_THREADS"])
     with open(os.path.join(HERE, name + ".json"), "w") as f:
         json.dump(G, f, indent=0)
@@ -49,8 +99,8 @@ def main_only(which):
     cases = {
         "tp3_bm_960_full": lambda: record("tp3_bm_960_full", deck_text("clover_bm.in")),
         "tp5_bm16_3840_full": lambda: record("tp5_bm16_3840_full", deck_text("clover_bm16.in")),
-        "bm64_short_7680_first10": lambda: record("bm64_short_7680_first10", deck_text("clover_bm64_short.in"), end_step=10),
-        "bm256_short_15360_first10": lambda: record("bm256_short_15360_first10", deck_text("clover_bm256_short.in"), end_step=10),
+        "bm64_short_7680_first10": lambda: record("bm64_short_7680_first10", deck_text("clover_bm64_short.in"), end_step=10, exact=True),
+        "bm256_short_15360_first10": lambda: record("bm256_short_15360_first10", deck_text("clover_bm256_short.in"), end_step=10, exact=True),
     }
     cases[which]()
 

@@ -147,8 +147,19 @@ def test_bm64_bm256_first_steps(fresh, name, deck):
     """The two large BASELINE configurations (7680^2, 15360^2) on one GPU: the first 10 steps (dt bit-identical,
     two summary rows) against the committed traces of the reference's C kernels.  15360^2 exercises the banded
     tile order (chunks wider than 4096 columns)."""
-    d = _run_against_golden(name, deck, end_step=10)
+    d = Driver(deck, cloverleaf_b200.LIB_B200, end_step=10)
+    d.run()
+    G = json.load(open(os.path.join(GOLDEN, name + ".json")))
+    # The reference accumulates its sums serially in fp64; at these sizes that alone carries 2e-10 .. 1e-9 relative
+    # rounding (its mass reads 28.000000005 for an exact 28), so against its printed sums only 1e-8 can be asked --
+    _check_against(G["dt"], G["summaries"], d, tol=1e-8)
+    # -- and the 1e-10 bar (1e-12 here) is held against the same per-cell terms of the reference run's own fields
+    # summed in 80-bit pairwise arithmetic (tests/golden/make_golden.py: exact_summary).
+    s = d.summaries()  # rows: start-up (step 0), the periodic one of step 10, the final one (step 10 again)
+    assert [int(r["step"]) for r in G["summaries_exact"]] == [0, 10] and [int(r["step"]) for r in s] == [0, 10, 10]
+    for a, b in zip([s[0], s[1], s[2]], [G["summaries_exact"][0], G["summaries_exact"][1], G["summaries_exact"][1]]):
+        for k in ("volume", "mass", "density", "pressure", "ie", "ke", "total"):
+            assert abs(a[k] - b[k]) <= 1e-12 * max(abs(b[k]), 1e-300), (b["step"], k, a[k], b[k])
     assert d.step == 10
-    s = d.summaries()
     assert abs(s[-1]["volume"] - 100.0) < 1e-9
     assert abs(s[-1]["mass"] / s[0]["mass"] - 1.0) < 1e-12
