@@ -239,6 +239,7 @@ def _main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3)
+    ap.add_argument("--trace", default="", help="write the in-situ launch timeline of 3 steps per rank to PREFIX.rankN.csv")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -344,6 +345,13 @@ def _main():
     cells = nx * ny
     value = cells * done / (ms * 1e-3)
     ms_per_step = ms / done
+
+    # ---- in-situ timeline of three steps (globaltimer stamps inside the kernels; launches NOT serialised)
+    if args.trace:
+        on = ci(1)
+        lib.clover_b200_trace_(ctypes.byref(on))
+        d.run(3)
+        lib.clover_b200_trace_dump_(("%s.rank%d.csv" % (args.trace, rank)).encode())
 
     # ---- per-kernel launch durations (CUDA events around every launch; outside the timed region)
     prof = {}

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(TX* TY, CPS)
     advec_mom_tma_kernel(const __grid_constant__ MomMaps M, const double* __restrict__ va_old, double* __restrict__ va_new,
                          const double* __restrict__ vb_old, double* __restrict__ vb_new,
                          const double* __restrict__ celld, int nx, int ny, int pitch, int ntx, int ntiles,
-                        const int2* __restrict__ order, int dep_start) {
+                        const int2* __restrict__ order, Tickets tickets, int dep_start, unsigned long long* trace) {
   using Cfg = MomCfg<DIR, TX, TY, RPT, STAGES, CPS>;
   constexpr int NT = Cfg::NT, W = Cfg::W, H = Cfg::H, BW = Cfg::BW, NI = Cfg::NI, OX = Cfg::OX, OY = Cfg::OY;
   extern __shared__ unsigned char smem_raw[];
@@ -84,37 +84,43 @@ __global__ void __launch_bounds__(TX* TY, CPS)
   const int tid = threadIdx.x, lx = tid % TX, ty = tid / TX;
   const int G = gridDim.x;
   pdl_trigger();
-  PdlGate gate(dep_start);
+  PdlGate gate(dep_start, trace);
   auto issue_tile = [&](int stage, int2 xy) {
     const int j0 = 1 + xy.x * W, k0 = 1 + xy.y * H;
     ring.issue(M.m, stage, j0 - OX + XOFF, k0 - OY + 1);
   };
+  __shared__ int s_tile[STAGES];
+  __shared__ int2 s_xy[STAGES];
+  TileQueue<STAGES> queue(tickets, ntiles, order, s_tile, s_xy);
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-      const int t = (int)blockIdx.x + s * G;
-      if (t < ntiles) {
+      int t;
+      int2 xy;
+      if (queue.draw(s, t, xy)) {
         gate.need(t);
-        issue_tile(s, __ldg(order + t));
+        issue_tile(s, xy);
       }
     }
   }
+  __syncthreads();
   // the sweep axis in box / plane coordinates: moving one node along the sweep
   constexpr int SB = DIR == 1 ? 1 : BW;   // box stride along the sweep
   constexpr int SP = DIR == 1 ? 1 : TX;   // plane stride along the sweep
-  // tile coordinates: host-built order table (tile_order, tma.cuh), fetched one iteration before they are needed
-  int2 cur = __ldg(order + blockIdx.x), nxt = cur, iss = make_int2(0, 0), iss_nxt = iss;
-  if ((int)blockIdx.x + (STAGES - 1) * G < ntiles) iss = __ldg(order + blockIdx.x + (STAGES - 1) * G);
-  int it = 0;
-  for (int t = blockIdx.x; t < ntiles; t += G, ++it, cur = nxt, iss = iss_nxt) {
+  for (int it = 0;; ++it) {
     const int stage = it % STAGES;
-    gate.need(t + (STAGES - 1) * G);
+    const int t = s_tile[stage];
+    if (t >= ntiles) break;
+    const int2 cur = s_xy[stage];
+    gate.need(t);
     if (tid == 0) {
-      const int tn = t + (STAGES - 1) * G;
-      if (tn < ntiles) issue_tile((stage + STAGES - 1) % STAGES, iss);
+      int tn;
+      int2 xy;
+      if (queue.draw((stage + STAGES - 1) % STAGES, tn, xy)) {
+        gate.need(tn);
+        issue_tile((stage + STAGES - 1) % STAGES, xy);
+      }
     }
-    nxt = (t + G < ntiles) ? __ldg(order + t + G) : cur;
-    iss_nxt = (t + STAGES * G < ntiles) ? __ldg(order + t + STAGES * G) : iss;
     const int j0 = 1 + cur.x * W, k0 = 1 + cur.y * H;
     // celldx / celldy at the sweep positions s-1, s, s+1 of my nodes (1-D, lower bound -1 -> index s+1; clamped for
     // the nodes beyond the chunk, whose results are never stored); issued before the wait so that they overlap it
@@ -253,7 +259,8 @@ static void launch_mom(const Grid& g, const MomMaps& M, const double* va_old, do
   const TileOrder ord = tile_order_split(ntx, nty, Cfg::W, Cfg::H, Cfg::OX, Cfg::BW - Cfg::OX - Cfg::W, Cfg::OY,
                                          Cfg::BH - Cfg::OY - Cfg::H, g.nx, g.ny);
   launch_pdl(advec_mom_tma_kernel<DIR, MS, TX, TY, RPT, STAGES, CPS>, dim3(ctas), dim3(Cfg::NT), Cfg::SMEM, stream(), M, va_old,
-             va_new, vb_old, vb_new, celld, g.nx, g.ny, g.pitch, ntx, ntiles, ord.table, dep_start_for(ord));
+             va_new, vb_old, vb_new, celld, g.nx, g.ny, g.pitch, ntx, ntiles, ord.table, next_tickets(ntiles, ctas),
+             dep_start_for(ord), current_trace());
 }
 
 // ====================================================================================================================
@@ -288,7 +295,8 @@ __global__ void __launch_bounds__(TX* TY, CPS)
     advec_cell_tma_kernel(const __grid_constant__ CellMaps M, const double* __restrict__ d_old, double* __restrict__ d_new,
                           const double* __restrict__ e_old, double* __restrict__ e_new,
                           double* __restrict__ mass_flux, const double* __restrict__ vertexd, int nx, int ny, int pitch,
-                          int ntx, int nty, const int2* __restrict__ order, int dep_start) {
+                          int ntx, int nty, const int2* __restrict__ order, Tickets tickets, int dep_start,
+                          unsigned long long* trace) {
   using Cfg = CellCfg<DIR, TX, TY, RPT, STAGES, CPS>;
   constexpr int NT = Cfg::NT, W = Cfg::W, H = Cfg::H, BW = Cfg::BW, NI = Cfg::NI, OX = Cfg::OX, OY = Cfg::OY;
   constexpr int NS = DIR == 1 ? W : H;             // cells of a tile along the sweep
@@ -304,37 +312,43 @@ __global__ void __launch_bounds__(TX* TY, CPS)
   const int G = gridDim.x;
   const int ntiles = ntx * nty;
   pdl_trigger();
-  PdlGate gate(dep_start);
+  PdlGate gate(dep_start, trace);
   auto issue_tile = [&](int stage, int2 xy) {
     const int j0 = 1 + xy.x * W, k0 = 1 + xy.y * H;
     ring.issue(M.m, stage, j0 - OX + XOFF, k0 - OY + 1);
   };
+  __shared__ int s_tile[STAGES];
+  __shared__ int2 s_xy[STAGES];
+  TileQueue<STAGES> queue(tickets, ntiles, order, s_tile, s_xy);
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-      const int t = (int)blockIdx.x + s * G;
-      if (t < ntiles) {
+      int t;
+      int2 xy;
+      if (queue.draw(s, t, xy)) {
         gate.need(t);
-        issue_tile(s, __ldg(order + t));
+        issue_tile(s, xy);
       }
     }
   }
+  __syncthreads();
   constexpr int SB = DIR == 1 ? 1 : BW;  // box stride along the sweep
   constexpr int SP = DIR == 1 ? 1 : TX;  // plane stride along the sweep
   const int smax = (DIR == 1 ? nx : ny) + 2;
-  // tile coordinates: host-built order table (tile_order, tma.cuh), fetched one iteration before they are needed
-  int2 cur = __ldg(order + blockIdx.x), nxt = cur, iss = make_int2(0, 0), iss_nxt = iss;
-  if ((int)blockIdx.x + (STAGES - 1) * G < ntiles) iss = __ldg(order + blockIdx.x + (STAGES - 1) * G);
-  int it = 0;
-  for (int t = blockIdx.x; t < ntiles; t += G, ++it, cur = nxt, iss = iss_nxt) {
+  for (int it = 0;; ++it) {
     const int stage = it % STAGES;
-    gate.need(t + (STAGES - 1) * G);
+    const int t = s_tile[stage];
+    if (t >= ntiles) break;
+    const int2 cur = s_xy[stage];
+    gate.need(t);
     if (tid == 0) {
-      const int tn = t + (STAGES - 1) * G;
-      if (tn < ntiles) issue_tile((stage + STAGES - 1) % STAGES, iss);
+      int tn;
+      int2 xy;
+      if (queue.draw((stage + STAGES - 1) % STAGES, tn, xy)) {
+        gate.need(tn);
+        issue_tile((stage + STAGES - 1) % STAGES, xy);
+      }
     }
-    nxt = (t + G < ntiles) ? __ldg(order + t + G) : cur;
-    iss_nxt = (t + STAGES * G < ntiles) ? __ldg(order + t + STAGES * G) : iss;
     const int tx_ = cur.x, ty_ = cur.y;
     const int j0 = 1 + tx_ * W, k0 = 1 + ty_ * H;
     const bool last_along = DIR == 1 ? (tx_ == ntx - 1) : (ty_ == nty - 1);
@@ -449,7 +463,8 @@ static void launch_cell(const Grid& g, const CellMaps& M, const double* d_old, d
   const TileOrder ord = tile_order_split(ntx, nty, Cfg::W, Cfg::H, Cfg::OX, Cfg::BW - Cfg::OX - Cfg::W, Cfg::OY,
                                          Cfg::BH - Cfg::OY - Cfg::H, g.nx, g.ny);
   launch_pdl(advec_cell_tma_kernel<DIR, SWEEP, TX, TY, RPT, STAGES, CPS>, dim3(ctas), dim3(Cfg::NT), Cfg::SMEM, stream(), M, d_old,
-             d_new, e_old, e_new, mass_flux, vertexd, g.nx, g.ny, g.pitch, ntx, nty, ord.table, dep_start_for(ord));
+             d_new, e_old, e_new, mass_flux, vertexd, g.nx, g.ny, g.pitch, ntx, nty, ord.table, next_tickets(ntiles, ctas),
+             dep_start_for(ord), current_trace());
 }
 
 void run_advec_cell_tma(const Grid& g, int dir, int sweep, double* vertexdx, double* vertexdy, double* volume,

@@ -134,13 +134,13 @@ __global__ void __launch_bounds__(BX* BY, TT_CPS)
                         const double* __restrict__ energy0, double* __restrict__ pressure,
                         double* __restrict__ viscosity, double* __restrict__ soundspeed, double* __restrict__ partials,
                         unsigned int* ticket, double* __restrict__ out, int nx, int ny, int pitch, int ntx, int ntiles,
-                        const int2* __restrict__ order, int dep_start, ReduceTail RT) {
+                        const int2* __restrict__ order, Tickets tickets, int dep_start, unsigned long long* trace, ReduceTail RT) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = align128(smem_raw);
   TimestepRing ring;
   ring.init(smem);
   pdl_trigger();
-  PdlGate gate(dep_start);
+  PdlGate gate(dep_start, trace);
   const int lx = threadIdx.x, ly = threadIdx.y;
   const bool leader = (lx == 0 && ly == 0);
   const int G = gridDim.x;
@@ -149,29 +149,35 @@ __global__ void __launch_bounds__(BX* BY, TT_CPS)
     const int j0 = 1 + xy.x * TT_W, k0 = 1 + xy.y * TT_H;
     ring.issue(M.m, stage, j0 - 2 + XOFF, k0 - 1 + 1);
   };
+  __shared__ int s_tile[TT_STAGES];
+  __shared__ int2 s_xy[TT_STAGES];
+  TileQueue<TT_STAGES> queue(tickets, ntiles, order, s_tile, s_xy);
   if (leader) {
 #pragma unroll
     for (int s = 0; s < TT_STAGES - 1; ++s) {
-      const int t = (int)blockIdx.x + s * G;
-      if (t < ntiles) {
+      int t;
+      int2 xy;
+      if (queue.draw(s, t, xy)) {
         gate.need(t);
-        issue_tile(s, __ldg(order + t));
+        issue_tile(s, xy);
       }
     }
   }
-  // tile coordinates: host-built order table (tile_order, tma.cuh), fetched one iteration before they are needed
-  int2 cur = __ldg(order + blockIdx.x), nxt = cur, iss = make_int2(0, 0), iss_nxt = iss;
-  if ((int)blockIdx.x + (TT_STAGES - 1) * G < ntiles) iss = __ldg(order + blockIdx.x + (TT_STAGES - 1) * G);
-  int it = 0;
-  for (int t = blockIdx.x; t < ntiles; t += G, ++it, cur = nxt, iss = iss_nxt) {
+  __syncthreads();
+  for (int it = 0;; ++it) {
     const int stage = it % TT_STAGES;
-    gate.need(t + (TT_STAGES - 1) * G);  // rim tiles (and their loads, issued STAGES-1 tiles ahead) wait for the halo kernel
+    const int t = s_tile[stage];
+    if (t >= ntiles) break;
+    const int2 cur = s_xy[stage];
+    gate.need(t);  // rim tiles wait for the halo kernel (their loads, issued STAGES-1 tiles ahead, waited in the leader)
     if (leader) {
-      const int tn = t + (TT_STAGES - 1) * G;
-      if (tn < ntiles) issue_tile((stage + TT_STAGES - 1) % TT_STAGES, iss);
+      int tn;
+      int2 xy;
+      if (queue.draw((stage + TT_STAGES - 1) % TT_STAGES, tn, xy)) {
+        gate.need(tn);
+        issue_tile((stage + TT_STAGES - 1) % TT_STAGES, xy);
+      }
     }
-    nxt = (t + G < ntiles) ? __ldg(order + t + G) : cur;
-    iss_nxt = (t + TT_STAGES * G < ntiles) ? __ldg(order + t + TT_STAGES * G) : iss;
     const int j = 1 + cur.x * TT_W + lx, k = 1 + cur.y * TT_H + ly;
     const bool active = j <= nx && k <= ny;
     const int jc = j <= nx ? j : nx, kc = k <= ny ? k : ny;  // 1-D geometry of the threads beyond the chunk
@@ -293,13 +299,13 @@ template <bool WRITE_SS>
 __global__ void __launch_bounds__(BX* BY, PT_CPS)
     pdv_predict_eos_tma_kernel(const __grid_constant__ PredictMaps M, double dt, double* __restrict__ pressure,
                                double* __restrict__ soundspeed, int nx, int ny, int pitch, int ntx, int ntiles,
-                        const int2* __restrict__ order, int dep_start) {
+                        const int2* __restrict__ order, Tickets tickets, int dep_start, unsigned long long* trace) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = align128(smem_raw);
   PredictRing ring;
   ring.init(smem);
   pdl_trigger();
-  PdlGate gate(dep_start);
+  PdlGate gate(dep_start, trace);
   const int lx = threadIdx.x, ly = threadIdx.y;
   const bool leader = (lx == 0 && ly == 0);
   const int G = gridDim.x;
@@ -307,29 +313,35 @@ __global__ void __launch_bounds__(BX* BY, PT_CPS)
     const int j0 = 1 + xy.x * PT_W, k0 = 1 + xy.y * PT_H;
     ring.issue(M.m, stage, j0 + XOFF, k0 + 1);
   };
+  __shared__ int s_tile[PT_STAGES];
+  __shared__ int2 s_xy[PT_STAGES];
+  TileQueue<PT_STAGES> queue(tickets, ntiles, order, s_tile, s_xy);
   if (leader) {
 #pragma unroll
     for (int s = 0; s < PT_STAGES - 1; ++s) {
-      const int t = (int)blockIdx.x + s * G;
-      if (t < ntiles) {
+      int t;
+      int2 xy;
+      if (queue.draw(s, t, xy)) {
         gate.need(t);
-        issue_tile(s, __ldg(order + t));
+        issue_tile(s, xy);
       }
     }
   }
-  // tile coordinates: host-built order table (tile_order, tma.cuh), fetched one iteration before they are needed
-  int2 cur = __ldg(order + blockIdx.x), nxt = cur, iss = make_int2(0, 0), iss_nxt = iss;
-  if ((int)blockIdx.x + (PT_STAGES - 1) * G < ntiles) iss = __ldg(order + blockIdx.x + (PT_STAGES - 1) * G);
-  int it = 0;
-  for (int t = blockIdx.x; t < ntiles; t += G, ++it, cur = nxt, iss = iss_nxt) {
+  __syncthreads();
+  for (int it = 0;; ++it) {
     const int stage = it % PT_STAGES;
-    gate.need(t + (PT_STAGES - 1) * G);
+    const int t = s_tile[stage];
+    if (t >= ntiles) break;
+    const int2 cur = s_xy[stage];
+    gate.need(t);
     if (leader) {
-      const int tn = t + (PT_STAGES - 1) * G;
-      if (tn < ntiles) issue_tile((stage + PT_STAGES - 1) % PT_STAGES, iss);
+      int tn;
+      int2 xy;
+      if (queue.draw((stage + PT_STAGES - 1) % PT_STAGES, tn, xy)) {
+        gate.need(tn);
+        issue_tile((stage + PT_STAGES - 1) % PT_STAGES, xy);
+      }
     }
-    nxt = (t + G < ntiles) ? __ldg(order + t + G) : cur;
-    iss_nxt = (t + PT_STAGES * G < ntiles) ? __ldg(order + t + PT_STAGES * G) : iss;
     const int j = 1 + cur.x * PT_W + lx, k = 1 + cur.y * PT_H + ly;
     ring.wait(stage, (uint32_t)((it / PT_STAGES) & 1));
     const double* __restrict__ sxa = ring.tile(stage, PA_XAREA);
@@ -502,7 +514,8 @@ struct CorrectCfg {
 template <int W, int RPT, int STAGES, int CPS>
 __global__ void __launch_bounds__(W* LT_H / RPT, CPS)
     lagrange_correct_tma_kernel(const __grid_constant__ CorrectMaps M, CorrectOut O, int nx, int ny, int pitch,
-                                double dt, int ntx, int ntiles, const int2* __restrict__ order, int dep_start) {
+                                double dt, int ntx, int ntiles, const int2* __restrict__ order, Tickets tickets, int dep_start,
+                                unsigned long long* trace) {
   using Cfg = CorrectCfg<W, RPT, STAGES, CPS>;
   constexpr int NT = Cfg::NT, VPT = Cfg::VPT, NVERT = Cfg::NVERT, ROWS = LT_H / RPT, LT_W = W, LT_BW = Cfg::BW, LT_VW = Cfg::VW;
   extern __shared__ unsigned char smem_raw[];
@@ -510,7 +523,7 @@ __global__ void __launch_bounds__(W* LT_H / RPT, CPS)
   typename Cfg::Ring ring;
   ring.init(smem);
   pdl_trigger();
-  PdlGate gate(dep_start);
+  PdlGate gate(dep_start, trace);
   double* __restrict__ su1 = reinterpret_cast<double*>(smem + Cfg::Ring::BYTES);
   double* __restrict__ sv1 = su1 + NVERT;
   const int tid = threadIdx.x, lx = tid % LT_W, ty = tid / LT_W;
@@ -521,29 +534,35 @@ __global__ void __launch_bounds__(W* LT_H / RPT, CPS)
     const int j0 = 1 + xy.x * LT_W, k0 = 1 + xy.y * LT_H;
     ring.issue(M.m, stage, j0 - LT_OX + XOFF, k0 - 1 + 1);
   };
+  __shared__ int s_tile[STAGES];
+  __shared__ int2 s_xy[STAGES];
+  TileQueue<STAGES> queue(tickets, ntiles, order, s_tile, s_xy);
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-      const int t = (int)blockIdx.x + s * G;
-      if (t < ntiles) {
+      int t;
+      int2 xy;
+      if (queue.draw(s, t, xy)) {
         gate.need(t);
-        issue_tile(s, __ldg(order + t));
+        issue_tile(s, xy);
       }
     }
   }
-  // tile coordinates: host-built order table (tile_order, tma.cuh), fetched one iteration before they are needed
-  int2 cur = __ldg(order + blockIdx.x), nxt = cur, iss = make_int2(0, 0), iss_nxt = iss;
-  if ((int)blockIdx.x + (STAGES - 1) * G < ntiles) iss = __ldg(order + blockIdx.x + (STAGES - 1) * G);
-  int it = 0;
-  for (int t = blockIdx.x; t < ntiles; t += G, ++it, cur = nxt, iss = iss_nxt) {
+  __syncthreads();
+  for (int it = 0;; ++it) {
     const int stage = it % STAGES;
-    gate.need(t + (STAGES - 1) * G);
-    if (tid == 0) {
-      const int tn = t + (STAGES - 1) * G;  // its stage was released by the barrier that ended iteration it-1
-      if (tn < ntiles) issue_tile((stage + STAGES - 1) % STAGES, iss);
+    const int t = s_tile[stage];
+    if (t >= ntiles) break;
+    const int2 cur = s_xy[stage];
+    gate.need(t);
+    if (tid == 0) {  // the stage it refills was released by the barrier that ended iteration it-1
+      int tn;
+      int2 xy;
+      if (queue.draw((stage + STAGES - 1) % STAGES, tn, xy)) {
+        gate.need(tn);
+        issue_tile((stage + STAGES - 1) % STAGES, xy);
+      }
     }
-    nxt = (t + G < ntiles) ? __ldg(order + t + G) : cur;
-    iss_nxt = (t + STAGES * G < ntiles) ? __ldg(order + t + STAGES * G) : iss;
     const int j0 = 1 + cur.x * LT_W, k0 = 1 + cur.y * LT_H;
     ring.wait(stage, (uint32_t)((it / STAGES) & 1));
     const double* __restrict__ sxa = ring.tile(stage, LA_XAREA);
@@ -662,7 +681,7 @@ static void launch_correct_tma(const CorrectArgs& A, const Grid& g, double dt) {
   const int ctas = ntiles < cap ? ntiles : cap;
   const TileOrder ord = tile_order_split(ntx, nty, LT_W, LT_H, LT_OX, Cfg::BW - LT_OX - LT_W, 1, LT_BH - 1 - LT_H, g.nx, g.ny);
   launch_pdl(lagrange_correct_tma_kernel<W, RPT, STAGES, CPS>, dim3(ctas), dim3(Cfg::NT), Cfg::SMEM, stream(), M, O, g.nx, g.ny,
-             g.pitch, dt, ntx, ntiles, ord.table, dep_start_for(ord));
+             g.pitch, dt, ntx, ntiles, ord.table, next_tickets(ntiles, ctas), dep_start_for(ord), current_trace());
 }
 
 // single-call host launchers (lagrange.cu, advec.cu)
@@ -833,7 +852,8 @@ static size_t fuse_timestep(const Op* q, size_t n, size_t i) {
       LaunchScope ls("timestep_tma");
       const TileOrder ord = tile_order_split(ntx, nty, TT_W, TT_H, 2, TT_BW - 2 - TT_W, 1, TT_BH - 1 - TT_H, g.nx, g.ny);
       launch_pdl(timestep_tma_kernel<true>, dim3(ctas), dim3(BX, BY), TT_SMEM, stream(), M, P, cdx, cdy, d0, e0, p, qv, ss, part,
-                 ticket(), host_scalars(), g.nx, g.ny, g.pitch, ntx, ntiles, ord.table, dep_start_for(ord), RT);
+                 ticket(), host_scalars(), g.nx, g.ny, g.pitch, ntx, ntiles, ord.table, next_tickets(ntiles, ctas), dep_start_for(ord),
+                 ls.trace, RT);
     } else {
     const dim3 grid = persistent_grid(r, 1, g_ctas_per_sm_timestep[0]);
     double* part = partials((size_t)grid.x * grid.y);
@@ -906,12 +926,13 @@ static size_t fuse_predict(const Op* q, size_t n, size_t i) {
       LaunchScope ls("pdv_predict_tma");
       const TileOrder ord = tile_order_split(ntx, nty, PT_W, PT_H, 0, PT_BW - PT_W, 0, PT_BH - PT_H, g.nx, g.ny);
       const int dep = dep_start_for(ord);
+      const Tickets tk = next_tickets(ntiles, ctas);
       if (write_ss)
         launch_pdl(pdv_predict_eos_tma_kernel<true>, dim3(ctas), dim3(BX, BY), PT_SMEM, stream(), M, pv.sv[0], p, ss, g.nx, g.ny,
-                   g.pitch, ntx, ntiles, ord.table, dep);
+                   g.pitch, ntx, ntiles, ord.table, tk, dep, ls.trace);
       else
         launch_pdl(pdv_predict_eos_tma_kernel<false>, dim3(ctas), dim3(BX, BY), PT_SMEM, stream(), M, pv.sv[0], p, ss, g.nx, g.ny,
-                   g.pitch, ntx, ntiles, ord.table, dep);
+                   g.pitch, ntx, ntiles, ord.table, tk, dep, ls.trace);
     } else {
     const Range r = make_range(1, g.nx, 1, g.ny);
     const dim3 grid = grid_for(r, NR_PRED);

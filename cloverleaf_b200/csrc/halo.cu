@@ -96,11 +96,14 @@ __device__ __forceinline__ void update_halo_item(const FieldDesc& F, int nx, int
 }
 __global__ void __launch_bounds__(256)
     update_halo_kernel(FieldTable T, int nx, int ny, int pitch, int depth, int ext_left, int ext_right,
-                       int ext_bottom, int ext_top) {
+                       int ext_bottom, int ext_top, unsigned long long* trace) {
+  trace_min(trace, 0);
   pdl_wait();     // the kernel that produced the interior cells has completed
   pdl_trigger();  // the next compute kernel may start its interior tiles (common.cuh: PDL)
+  trace_min(trace, 2);
   update_halo_item(T.f[blockIdx.y], nx, ny, pitch, depth, ext_left, ext_right, ext_bottom, ext_top,
                    (int)(blockIdx.x * blockDim.x + threadIdx.x));
+  trace_max(trace, 1);
 }
 
 // Chunks narrower than depth+1 cells: the mirror source of a depth-2 halo cell can itself be a halo cell that an
@@ -460,22 +463,38 @@ __device__ __forceinline__ void corner_index(const FieldDesc& F, int nx, int ny,
   }
 }
 
+// A few CTAs move all strips: every thread keeps XU independent loads in flight (the copy is latency-bound: the
+// strips are a few hundred KB, the sources are strided rows of the fields or the peers' freshly written slots).
+constexpr int XU = 4;
 template <bool UNPACK>
 __device__ __forceinline__ void exchange_copy(const FieldTable& T, int nx, int ny, int pitch, int depth, const XArgs& A,
                                               int gtid, int gsize) {
   for (int z = 0; z < A.nface; ++z) {
     const int face = A.face[z];
     const int per_field = ((face < 2 ? ny : nx) + 1 + 2 * depth) * depth;
-    for (int i = gtid; i < per_field * T.n; i += gsize) {
-      const int f = i / per_field, t = i - f * per_field;
-      const FieldDesc& F = T.f[f];
-      int j, k, index;
-      bool valid;
-      message_index(F, nx, ny, depth, face, UNPACK, t, j, k, index, valid);
-      if (valid) {
-        if (UNPACK) F.p[idx2(pitch, j, k)] = __ldcg(A.fmine[z] + index);
-        else        A.fbuf[z][index] = F.p[idx2(pitch, j, k)];
+    const int total = per_field * T.n;
+    for (int i0 = gtid; i0 < total; i0 += gsize * XU) {
+      double v[XU];
+      double* dst[XU];
+#pragma unroll
+      for (int u = 0; u < XU; ++u) {
+        const int i = i0 + u * gsize;
+        dst[u] = nullptr;
+        if (i < total) {
+          const int f = i / per_field, t = i - f * per_field;
+          const FieldDesc& F = T.f[f];
+          int j, k, index;
+          bool valid;
+          message_index(F, nx, ny, depth, face, UNPACK, t, j, k, index, valid);
+          if (valid) {
+            if (UNPACK) { v[u] = __ldcg(A.fmine[z] + index); dst[u] = F.p + idx2(pitch, j, k); }
+            else        { v[u] = F.p[idx2(pitch, j, k)];     dst[u] = A.fbuf[z] + index; }
+          }
+        }
       }
+#pragma unroll
+      for (int u = 0; u < XU; ++u)
+        if (dst[u]) *dst[u] = v[u];
     }
   }
   const int per_corner = depth * depth;
@@ -523,9 +542,11 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 __global__ void __launch_bounds__(256)
     halo_exchange_kernel(FieldTable T, int nx, int ny, int pitch, int depth, XArgs A, unsigned int* counters,
                          unsigned int arrive_target, unsigned int barrier_target, int4 ext, unsigned long long timeout_ns,
-                         double* err, int rank) {
+                         double* err, int rank, unsigned long long* trace) {
+  trace_min(trace, 0);
   pdl_wait();     // the kernel that produced the strips has completed
   pdl_trigger();  // the next compute kernel may start: its interior tiles need none of what follows (common.cuh: PDL)
+  trace_min(trace, 2);  // [2] = work begins (dependency satisfied); [3] = all neighbours' strips have arrived
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
   if (A.nflag > 0) {
     exchange_copy<false>(T, nx, ny, pitch, depth, A, gtid, gsize);
@@ -539,6 +560,7 @@ __global__ void __launch_bounds__(256)
           asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.flag_out[z]), "l"(A.seq) : "memory");
       }
       for (int z = 0; z < A.nflag; ++z) spin_until_ge(A.flag_in[z], A.seq, timeout_ns, err, 1, rank, z);
+      trace_max(trace, 3);
     }
     __syncthreads();
     exchange_copy<true>(T, nx, ny, pitch, depth, A, gtid, gsize);
@@ -551,6 +573,7 @@ __global__ void __launch_bounds__(256)
     for (int i = gtid; i < ring * T.n; i += gsize)
       update_halo_item(T.f[i / ring], nx, ny, pitch, depth, ext.x, ext.y, ext.z, ext.w, i % ring);
   }
+  trace_max(trace, 1);
 }
 
 static bool p2p_setup(const Grid& g) {
@@ -741,13 +764,15 @@ static void p2p_exchange(const Grid& g, const HaloArgs& h, const HaloArgs* bc) {
     const long long ring = (long long)T.n * (2 * h.depth * (g.nx + 1 + 2 * h.depth) + 2 * h.depth * (g.ny + 1));
     if (ring > elements) elements = ring;
   }
+  // Few CTAs on purpose: the exchange runs NEXT TO the interior tiles of the compute kernel that follows it (PDL), and
+  // every SM it sits on can hold one compute CTA less while it runs.  $CLOVER_B200_XCTAS overrides (A/B runs).
   static int max_ctas = 0;
   if (!max_ctas) {
-    max_ctas = sm_count();
+    max_ctas = 32;
     if (const char* e = getenv("CLOVER_B200_XCTAS")) max_ctas = atoi(e) > 0 ? atoi(e) : max_ctas;
     if (max_ctas > sm_count()) max_ctas = sm_count();
   }
-  int ctas = (int)((elements + 256 * 4 - 1) / (256 * 4));
+  int ctas = (int)((elements + 256 * XU - 1) / (256 * XU));
   if (ctas < 1) ctas = 1;
   if (ctas > max_ctas) ctas = max_ctas;
   unsigned int* counters = (unsigned int*)(PP.mine + 256);
@@ -756,7 +781,7 @@ static void p2p_exchange(const Grid& g, const HaloArgs& h, const HaloArgs* bc) {
   {
     LaunchScope ls("halo_exchange_p2p");
     launch_pdl(halo_exchange_kernel, dim3((unsigned)ctas), dim3(256), 0, stream(), T, g.nx, g.ny, g.pitch, h.depth, A, counters,
-               PP.arrive_total, PP.barrier_total, ext, spin_timeout_ns(), device_error_record(), N.rank);
+               PP.arrive_total, PP.barrier_total, ext, spin_timeout_ns(), device_error_record(), N.rank, ls.trace);
   }
   note_halo_launch();
 }
@@ -803,7 +828,7 @@ void run_update_halo(const Grid& g, const HaloArgs& h) {
     {
       LaunchScope ls("update_halo");
       launch_pdl(update_halo_kernel, grid, dim3(256), 0, stream(), T, g.nx, g.ny, g.pitch, h.depth, h.ext[0], h.ext[1],
-                 h.ext[2], h.ext[3]);
+                 h.ext[2], h.ext[3], ls.trace);
     }
     note_halo_launch();
   }

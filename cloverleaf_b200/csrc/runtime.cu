@@ -77,12 +77,19 @@ struct Runtime {
   bool pdl = true;        // programmatic dependent launch ($CLOVER_B200_PDL=0 disables)
   bool split = true;      // interior tiles before the halo wait ($CLOVER_B200_SPLIT=0: wait before the first tile)
   bool halo_noted = false;  // the last launch was an exchange / update_halo kernel
+  unsigned int ticket_issued[4] = {0, 0, 0, 0};
+  unsigned int ticket_turn = 0;
+  bool trace_on = false;                 // in-situ timeline (clover_b200_trace_)
+  unsigned long long* d_trace = nullptr;  // 4 stamps per launch
+  std::vector<const char*> trace_names;
+  unsigned long long* cur_trace = nullptr;  // slot of the launch whose LaunchScope is open
   unsigned long long scalar_seq = 0;               // sequence number of the reduction results in h_scalars
   unsigned long long spin_timeout_ns = 20000000000ull;  // device-side waits for other GPUs ($CLOVER_B200_SPIN_TIMEOUT_MS)
   std::map<std::string, Prof> prof;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
+constexpr size_t TRACE_CAP = 1 << 16;
 Runtime R;
 
 void drop_tensor_maps();  // defined with the tensor-map cache below
@@ -420,12 +427,19 @@ void finish() {
   CLV_CUDA(cudaStreamSynchronize(R.stream));
 }
 
-LaunchScope::LaunchScope(const char* n) : name(n) {
+LaunchScope::LaunchScope(const char* n) : name(n), trace(nullptr) {
   if (R.profiling) CLV_CUDA(cudaEventRecord(R.ev0, R.stream));
+  if (R.trace_on && R.trace_names.size() < TRACE_CAP) {
+    trace = R.d_trace + 4 * R.trace_names.size();
+    R.trace_names.push_back(n);
+  }
+  R.cur_trace = trace;
 }
+unsigned long long* current_trace() { return R.cur_trace; }
 
 LaunchScope::~LaunchScope() {
   R.launches++;
+  R.cur_trace = nullptr;
   R.halo_noted = false;  // halo.cu re-notes after its scope closes; any other launch ends the "just launched" state
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) fatal("launch of %s failed: %s", name, cudaGetErrorString(e));
@@ -627,6 +641,18 @@ TileOrder tile_order_split(int ntx, int nty, int tw, int th, int lo_x, int hi_x,
   return o;
 }
 
+// Ticket counters of the dynamic tile queues (tma.cuh): four device counters used in turn (at most two consecutive
+// launches ever draw at the same time: a dependent's CTAs start while its predecessor's last CTAs are finishing),
+// never reset; the host mirrors their values (uint32 arithmetic wraps consistently on both sides).
+Tickets next_tickets(int ntiles, int ctas) {
+  const int i = R.ticket_turn++ & 3;
+  Tickets t;
+  t.counter = R.d_ticket + 8 + i;
+  t.base = R.ticket_issued[i];
+  R.ticket_issued[i] += (unsigned int)ntiles + (unsigned int)ctas;
+  return t;
+}
+
 // ---- programmatic dependent launch bookkeeping (common.cuh) ----------------------------------------------------
 bool pdl_enabled() { return R.pdl && !R.profiling; }
 void note_halo_launch() { R.halo_noted = true; }
@@ -669,6 +695,8 @@ void clover_b200_init_(int* device) {
   CLV_CUDA(cudaHostAlloc(&R.h_scalars, 64 * sizeof(double), cudaHostAllocMapped));
   CLV_CUDA(cudaMalloc(&R.d_ticket, 16 * sizeof(unsigned int)));
   CLV_CUDA(cudaMemset(R.d_ticket, 0, 16 * sizeof(unsigned int)));
+  for (int i = 0; i < 4; ++i) R.ticket_issued[i] = 0;
+  R.ticket_turn = 0;
   CLV_CUDA(cudaEventCreate(&R.ev0));
   CLV_CUDA(cudaEventCreate(&R.ev1));
   if (const char* s = getenv("CLOVER_B200_PDL")) R.pdl = (atoi(s) != 0);
@@ -839,6 +867,54 @@ void clover_b200_set_tma_(int* on) {
 }
 
 void clover_b200_profile_reset_(void) { R.prof.clear(); }
+
+// In-situ timeline: with *on != 0 every launch from now on gets a slot of four %globaltimer stamps (common.cuh);
+// trace_dump_ writes "index,name,start_ns,end_ns,wait_begin_ns,wait_end_ns" (relative to the first start; empty
+// fields where a kernel has no such stamp) and clears the record.  Unlike the event profile this does not serialise
+// the launches: it shows the step as it really runs (overlap of the halo exchange with interior tiles, gaps).
+void clover_b200_trace_(int* on) {
+  ensure_init();
+  flush_deferred();
+  join_side();
+  CLV_CUDA(cudaStreamSynchronize(R.stream));
+  if (*on && !R.d_trace) CLV_CUDA(cudaMalloc(&R.d_trace, TRACE_CAP * 4 * sizeof(unsigned long long)));
+  if (*on) {
+    std::vector<unsigned long long> init(TRACE_CAP * 4);
+    for (size_t i = 0; i < TRACE_CAP; ++i) { init[4 * i] = ~0ull; init[4 * i + 1] = 0; init[4 * i + 2] = ~0ull; init[4 * i + 3] = 0; }
+    CLV_CUDA(cudaMemcpy(R.d_trace, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    R.trace_names.clear();
+  }
+  R.trace_on = (*on != 0);
+}
+void clover_b200_trace_dump_(const char* path) {
+  ensure_init();
+  flush_deferred();
+  join_side();
+  CLV_CUDA(cudaStreamSynchronize(R.stream));
+  const size_t n = R.trace_names.size();
+  std::vector<unsigned long long> h(4 * (n ? n : 1));
+  if (n) CLV_CUDA(cudaMemcpy(h.data(), R.d_trace, 4 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  FILE* f = fopen(path, "w");
+  if (!f) fatal("trace_dump: cannot write %s", path);
+  unsigned long long t0 = ~0ull;
+  for (size_t i = 0; i < n; ++i)
+    if (h[4 * i] < t0) t0 = h[4 * i];
+  fprintf(f, "index,name,start_ns,end_ns,wait_begin_ns,wait_end_ns\n");
+  for (size_t i = 0; i < n; ++i) {
+    fprintf(f, "%zu,%s,", i, R.trace_names[i]);
+    if (h[4 * i] != ~0ull) fprintf(f, "%llu", h[4 * i] - t0);
+    fprintf(f, ",");
+    if (h[4 * i + 1] != 0) fprintf(f, "%llu", h[4 * i + 1] - t0);
+    fprintf(f, ",");
+    if (h[4 * i + 2] != ~0ull) fprintf(f, "%llu", h[4 * i + 2] - t0);
+    fprintf(f, ",");
+    if (h[4 * i + 3] != 0) fprintf(f, "%llu", h[4 * i + 3] - t0);
+    fprintf(f, "\n");
+  }
+  fclose(f);
+  R.trace_names.clear();
+  R.trace_on = false;
+}
 
 void clover_b200_profile_get_(int* max, char* names32, double* total_ms, long long* calls, int* n) {
   int i = 0;

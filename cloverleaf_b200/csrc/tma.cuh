@@ -128,6 +128,46 @@ struct TileRing {
   __device__ __forceinline__ void wait(int stage, uint32_t parity) { mbar_wait(&full[stage], parity); }
 };
 
+// Dynamic tile scheduling for the persistent kernels: CTAs draw tickets from a device counter (one atomicAdd per
+// tile, by the CTA's leader, STAGES-1 tiles ahead of the tile being computed) instead of striding through the table.
+// Why: (1) CTAs that become resident late -- their SM slot was still held by the halo-exchange kernel they overlap
+// with (PDL) or by the tail of the previous kernel -- simply take fewer tiles instead of finishing late with a full
+// static share; (2) data-dependent tile costs (the zero-numerator / inactive-limiter short cuts) balance out.
+// The counter is never reset: the host passes `base` = its value before this launch; every CTA draws exactly one
+// ticket past the end, so a launch advances it by ntiles + gridDim.x (runtime.cu: next_tickets).  Tickets follow the
+// order table, so interior tiles still come first and tiles in flight at the same time are still neighbours.
+struct Tickets {
+  unsigned int* counter;
+  unsigned int base;
+};
+template <int STAGES>
+struct TileQueue {
+  Tickets tk;
+  int ntiles;
+  const int2* order;
+  bool exhausted;
+  int* s_tile;   // [STAGES] shared: tile index loaded into each ring stage (>= ntiles: none)
+  int2* s_xy;    // [STAGES] shared: its coordinates
+  __device__ __forceinline__ TileQueue(Tickets t, int n, const int2* o, int* st, int2* sx)
+      : tk(t), ntiles(n), order(o), exhausted(false), s_tile(st), s_xy(sx) {}
+  // leader only: draw the next ticket for ring slot `slot`; true (+ index, coordinates) if it is a tile
+  __device__ __forceinline__ bool draw(int slot, int& t, int2& xy) {
+    t = ntiles;
+    if (!exhausted) {
+      const unsigned int v = atomicAdd(tk.counter, 1u) - tk.base;
+      if (v < (unsigned int)ntiles) t = (int)v;
+      else exhausted = true;
+    }
+    s_tile[slot] = t;
+    if (t >= ntiles) return false;
+    xy = __ldg(order + t);
+    s_xy[slot] = xy;
+    return true;
+  }
+};
+// Host: ticket counter + base for a launch of `ctas` persistent CTAs over `ntiles` tiles (runtime.cu).
+Tickets next_tickets(int ntiles, int ctas);
+
 __device__ __forceinline__ unsigned char* align128(unsigned char* p) {
   return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 127) & ~(uintptr_t)127);
 }

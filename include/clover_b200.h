@@ -247,6 +247,11 @@ void clover_b200_profile_(int *on);
 /* Writes up to *max entries; names are 32-byte NUL-padded records; returns the number in *n. */
 void clover_b200_profile_get_(int *max, char *names32, double *total_ms, long long *calls, int *n);
 void clover_b200_profile_reset_(void);
+/* In-situ timeline: while on, every launch records %globaltimer stamps (first CTA start, last CTA end, begin and
+ * end of its wait for the preceding halo kernel / for the neighbours' strips) WITHOUT serialising the launches;
+ * trace_dump_ writes them as CSV (index,name,start_ns,end_ns,wait_begin_ns,wait_end_ns) and switches tracing off. */
+void clover_b200_trace_(int *on);
+void clover_b200_trace_dump_(const char *path);
 /* Bytes copied host->device and device->host so far (all modes). */
 void clover_b200_copy_bytes_(long long *h2d, long long *d2h);
 /* Bytes this rank has written into its neighbours' memory (halo strips + corner blocks) and the number of

@@ -68,6 +68,11 @@ else:
     nr, rk = ctypes.c_int(world), ctypes.c_int(rank)
     lib.clover_b200_comm_init_(ctypes.byref(nr), ctypes.byref(rk), idbuf)
     d = Driver(deck, cloverleaf_b200.LIB_B200, nchunks=world, rank=rank, comm_mode=1, end_step=steps)
+die_at = int(os.environ.get("CLV_DIE_AT", "0"))
+if die_at:
+    d.run(die_at)
+    if rank == 1:
+        os._exit(0)  # a rank that dies mid-run: its neighbours must abort with a diagnostic, not hang the GPU
 d.run()
 out = dict(rank=rank, dt=d.dts().tolist(), summaries=d.summaries(), chunk=d.chunk_info(0))
 with open(os.path.join(os.environ["CLV_OUT"], "rank%d.json" % rank), "w") as f:
@@ -157,3 +162,28 @@ def test_nccl_transport_matches_single_gpu(tmp_path):
     dt1, _ = _single(ORACLE_PORT, nx, ny, steps)
     for r in ranks:
         assert r["dt"] == dt1, "rank %d: dt differs from the oracle's single-chunk run" % r["rank"]
+
+
+@pytest.mark.gpu
+def test_dead_rank_aborts_the_others(tmp_path):
+    """A rank that disappears mid-run: the surviving rank's exchange kernel gives up after the spin time-out, leaves
+    an error record, traps, and the host aborts with a diagnostic -- instead of spinning on a flag for ever with a
+    GPU that no longer answers (the peer-memory protocol has no other failure channel)."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import time
+    import cloverleaf_b200
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, CLV_ROOT=ROOT, CLV_BACKEND="nccl", CLV_LIB=cloverleaf_b200.LIB_B200, CLV_NX="256",
+               CLV_NY="192", CLV_STEPS="30", CLV_OUT=str(tmp_path), OMP_NUM_THREADS="1", CLV_DIE_AT="7",
+               CLOVER_B200_SPIN_TIMEOUT_MS="3000")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
+    t0 = time.time()
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    took = time.time() - t0
+    assert r.returncode != 0
+    assert "device-side time-out" in r.stderr and "halo exchange" in r.stderr, r.stderr[-3000:]
+    assert not os.path.exists(tmp_path / "rank0.json")
+    assert took < 120, took
