@@ -44,14 +44,15 @@ ALG_BYTES_PER_CELL_STEP = 856.0  # 107 fp64 array passes
 # show.  `survey` = SURVEY.md section 8a "alg" passes of the reference calls the launch replaces (a fused launch
 # replaces several; their sum over a step is the fixed 107 passes = 856 B per cell-update of section 8d).
 KERNEL_PASSES = {
-    "ideal_gas": (4, 4), "viscosity": (5, 5), "calc_dt": (8, 8), "pdv_predict": (11, 11), "pdv_correct": (13, 13),
+    "ideal_gas": (4, 4), "soundspeed_lazy": (3, 3), "viscosity": (5, 5), "calc_dt": (8, 8), "pdv_predict": (11, 11), "pdv_correct": (13, 13),
     "revert": (4, 4), "accelerate": (10, 10), "flux_calc": (8, 8), "reset_field": (8, 8), "field_summary": (6, 6),
     "advec_cell_x": (7.5, 7.5), "advec_cell_y": (7.5, 7.5), "advec_cell_x_tma": (7.5, 7.5), "advec_cell_y_tma": (7.5, 7.5),
     "advec_mom_x": (4.25, 4.25), "advec_mom_y": (4.25, 4.25), "advec_mom_x2": (8.5, 8.5), "advec_mom_y2": (8.5, 8.5),
     "advec_mom_x_tma": (8.5, 8.5), "advec_mom_y_tma": (8.5, 8.5),
-    # fused launches (csrc/fuse.cu): ideal_gas+viscosity+calc_dt reads d0,e0,u0,v0,volume,xarea,yarea and writes p,q,c;
+    # fused launches (csrc/fuse.cu): ideal_gas+viscosity+calc_dt reads d0,e0,u0,v0,volume,xarea,yarea and writes p,q
+    # (the TMA variant leaves the sound speed unevaluated: nothing reads it before it is overwritten; the register variant writes it);
     # PdV predictor+ideal_gas+revert reads 9 fields and writes p; accelerate+PdV corrector+flux_calc reads 9, writes 6
-    "timestep_fused": (10, 17), "timestep_tma": (10, 17), "pdv_predict_fused": (10, 19), "pdv_predict_tma": (10, 19),
+    "timestep_fused": (10, 17), "timestep_tma": (9, 17), "pdv_predict_fused": (10, 19), "pdv_predict_tma": (10, 19),
     "lagrange_correct_fused": (15, 31), "lagrange_correct_tma": (15, 31),
 }
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
@@ -239,6 +240,9 @@ def _main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=3)
+    ap.add_argument("--active-skip", type=int, default=2000,
+                    help="steps of clover_bm16.in to run before the active-regime measurement (0: skip it)")
+    ap.add_argument("--active-steps", type=int, default=60)
     ap.add_argument("--trace", default="", help="write the in-situ launch timeline of 3 steps per rank to PREFIX.rankN.csv")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -354,12 +358,12 @@ def _main():
         lib.clover_b200_trace_dump_(("%s.rank%d.csv" % (args.trace, rank)).encode())
 
     # ---- per-kernel launch durations (CUDA events around every launch; outside the timed region)
-    prof = {}
-    if args.profile_steps > 0:
+    def profile_kernels(drv, nsteps):
+        prof = {}
         on, off = ci(1), ci(0)
         lib.clover_b200_profile_reset_()
         lib.clover_b200_profile_(ctypes.byref(on))
-        d.run(args.profile_steps)
+        drv.run(nsteps)
         lib.clover_b200_profile_(ctypes.byref(off))
         mx = ci(64); n = ci(0)
         names = ctypes.create_string_buffer(32 * 64)
@@ -368,19 +372,26 @@ def _main():
         for i in range(n.value):
             nm = names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode()
             prof[nm] = dict(ms_total=tot[i], calls=calls[i], ms_avg=tot[i] / max(calls[i], 1))
+        return prof
+
+    def kernel_table(prof, nsteps, ncells, peak):
+        out = {}
+        step_ms = sum(p["ms_total"] for p in prof.values()) / nsteps
+        for nm, p in sorted(prof.items(), key=lambda kv: -kv[1]["ms_total"]):
+            passes = KERNEL_PASSES.get(nm, (None, None))[0]
+            gbs = passes * 8.0 * ncells / (p["ms_avg"] * 1e-3) / 1e9 if passes else None
+            out[nm] = dict(ms_avg=round(p["ms_avg"], 5), calls_per_step=p["calls"] / nsteps,
+                           share=round(p["ms_total"] / nsteps / step_ms, 4),
+                           alg_gbs=round(gbs, 1) if gbs else None, frac=round(gbs / peak, 4) if gbs else None)
+        return out
+
+    prof = profile_kernels(d, args.profile_steps) if args.profile_steps > 0 else {}
     chunk_cells = d.chunk_info(0)["x_max"] * d.chunk_info(0)["y_max"]
     peak, peak_src = hbm_peak()
     roofline = None
     kernels = {}
     if prof:
-        step_ms = sum(p["ms_total"] for p in prof.values()) / args.profile_steps
-        for nm, p in sorted(prof.items(), key=lambda kv: -kv[1]["ms_total"]):
-            passes = KERNEL_PASSES.get(nm, (None, None))[0]
-            gbs = passes * 8.0 * chunk_cells / (p["ms_avg"] * 1e-3) / 1e9 if passes else None
-            kernels[nm] = dict(ms_avg=round(p["ms_avg"], 5), calls_per_step=p["calls"] / args.profile_steps,
-                               share=round(p["ms_total"] / args.profile_steps / step_ms, 4),
-                               alg_gbs=round(gbs, 1) if gbs else None,
-                               frac=round(gbs / peak, 4) if gbs else None)
+        kernels = kernel_table(prof, args.profile_steps, chunk_cells, peak)
         top = next(nm for nm in kernels if KERNEL_PASSES.get(nm))
         # dram bytes per launch of the same kernel from the committed ncu capture (same workload, 1 GPU), else null
         traffic = None
@@ -409,6 +420,24 @@ def _main():
             parity["ok"] = False
         parity["ranks_checked"] = world
     d.close()
+
+    # ---- the ACTIVE-mesh regime: the *_short decks stop after 87 steps, when the disturbance still
+    # covers <1 % of the mesh and the kernels' data-dependent short cuts (zero numerators, inactive limiters, non-
+    # compressing cells) are at their best.  The long deck of the same mesh, far into the run, is the other regime.
+    active = None
+    if args.active_skip > 0 and world == 1 and args.deck == "clover_bm16_short.in":
+        d3 = Driver(big_deck("clover_bm16.in"), cloverleaf_b200.LIB_B200)
+        d3.start()
+        d3.run(args.active_skip)
+        done3, ms3, _ = timed_steps(d3, args.active_steps)
+        prof3 = profile_kernels(d3, 3)
+        s3 = d3.field_summary()
+        active = {"deck": "clover_bm16.in %dx%d" % (nx, ny), "steps_skipped": args.active_skip, "steps": done3,
+                  "ms_per_step": ms3 / done3, "value": cells * done3 / (ms3 * 1e-3), "unit": "cell-updates/s",
+                  "vs_short_deck": (ms3 / done3) / ms_per_step, "ke_over_ie": s3["ke"] / s3["ie"],
+                  "kernels": {k: dict(ms_avg=v["ms_avg"], frac=v["frac"]) for k, v in
+                              kernel_table(prof3, 3, chunk_cells, peak).items() if v["frac"]}}
+        d3.close()
 
     # ---- end to end from host arrays (same C-ABI, resident mode, copies inside the timed region)
     # The whole deck as the user runs it: the complete state lives in (pinned) HOST arrays, as after the Fortran
@@ -487,7 +516,7 @@ def _main():
                               "achieved": round(step_gbs, 1), "peak": peak, "unit": "GB/s",
                               "frac": round(step_gbs / peak, 4), "frac_of_8TBs_nominal": round(step_gbs / 8000.0, 4),
                               "peak_source": peak_src},
-            "kernels": kernels, "cpu_baseline": cpu, "parity": parity,
+            "kernels": kernels, "active_regime": active, "cpu_baseline": cpu, "parity": parity,
         }
     # leave the device idle before the ranks part: nothing of ours may still be writing into a peer's memory
     lib.clover_b200_device_synchronize_()

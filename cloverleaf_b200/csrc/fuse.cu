@@ -111,6 +111,31 @@ __global__ void __launch_bounds__(BX* BY)
   block_reduce_publish<1, true>(m, partials, ticket, out, P.g_big, RT);
 }
 
+// One cell of T for the TMA kernel.  What only a compressing cell needs -- the four neighbour pressures and the
+// limiter of viscosity_kernel_c.c:60-104 -- is fetched from the staged tile and evaluated inside that minority branch;
+// the dt minimum takes the division-saving form (lagrange.cuh: calc_dt_cell_lean).  Same values as timestep_cell.
+struct TsCell {
+  double rho, en, u00, u10, u01, u11, v00, v10, v01, v11, vol, xa0, xa1, ya0, ya1, dsx, dsy, dsx1, dsy1;
+};
+template <bool SAFE>
+__device__ __forceinline__ double timestep_cell_lean(const TsCell& C, const double* __restrict__ sd,
+                                                     const double* __restrict__ se, int b, int bw, const DtParams& P,
+                                                     unsigned mask, double& p, double& ss, double& q, bool& bad) {
+  ideal_gas_cell<SAFE>(C.rho, C.en, p, ss, bad);
+  const double ugrad = (C.u10 + C.u11) - (C.u00 + C.u01);
+  const double vgrad = (C.v01 + C.v11) - (C.v00 + C.v10);
+  const double div = C.dsx * ugrad + C.dsy * vgrad;
+  q = 0.0;
+  if (!(div >= 0.0)) {  // viscosity_kernel_c.c:88: 0 unless compressing
+    const double pl = (1.4 - 1.0) * sd[b - 1] * se[b - 1], pr = (1.4 - 1.0) * sd[b + 1] * se[b + 1];
+    const double pb = (1.4 - 1.0) * sd[b - bw] * se[b - bw], pt = (1.4 - 1.0) * sd[b + bw] * se[b + bw];
+    const ViscIn V{C.u00, C.u10, C.u01, C.u11, C.v00, C.v10, C.v01, C.v11, C.dsx, C.dsy, C.dsx1, C.dsy1, pl, pr, pb, pt, C.rho};
+    q = viscosity_cell<SAFE>(V, bad);
+  }
+  const DtIn D{C.dsx, C.dsy, C.vol, ss, q, C.rho, C.u00, C.u10, C.u01, C.u11, C.v00, C.v10, C.v01, C.v11, C.xa0, C.xa1, C.ya0, C.ya1};
+  return calc_dt_cell_lean<SAFE>(D, P, bad, mask);
+}
+
 // ---- T with TMA tile staging (tma.cuh): persistent CTAs of 32x8 threads, one cell per thread, the seven input
 // fields of a 32x8 tile arrive as 36x10 boxes with corner (j0-2, k0-1).  Same arithmetic as timestep_kernel.
 constexpr int TT_W = BX, TT_H = BY, TT_BW = TT_W + 4, TT_BH = TT_H + 2, TT_NARR = 7;
@@ -191,44 +216,42 @@ __global__ void __launch_bounds__(BX* BY, TT_CPS)
     const double* __restrict__ sxa = ring.tile(stage, TA_XA);
     const double* __restrict__ sya = ring.tile(stage, TA_YA);
     const int b = (ly + 1) * TT_BW + lx + 2;
-    const double rho = sd[b], en = se[b];
-    const double rl = sd[b - 1], rr = sd[b + 1], rb = sd[b - TT_BW], rt = sd[b + TT_BW];
-    const double el = se[b - 1], er = se[b + 1], eb = se[b - TT_BW], et = se[b + TT_BW];
-    const double u00 = su[b], u10 = su[b + 1], u01 = su[b + TT_BW], u11 = su[b + TT_BW + 1];
-    const double v00 = sv[b], v10 = sv[b + 1], v01 = sv[b + TT_BW], v11 = sv[b + TT_BW + 1];
-    const double vol = svol[b];
-    const double xa0 = sxa[b], xa1 = sxa[b + 1], ya0 = sya[b], ya1 = sya[b + TT_BW];
-    __syncthreads();  // everything this tile needs is in registers: the stage can be refilled
-    // ideal_gas_kernel_c.c:52 for the four neighbours
-    const double pl = (1.4 - 1.0) * rl * el, pr = (1.4 - 1.0) * rr * er;
-    const double pb = (1.4 - 1.0) * rb * eb, pt = (1.4 - 1.0) * rt * et;
-    ViscIn V{u00, u10, u01, u11, v00, v10, v01, v11, dsx, dsy, dsx1, dsy1, pl, pr, pb, pt, rho};
-    DtIn D{dsx, dsy, vol, 0.0, 0.0, rho, u00, u10, u01, u11, v00, v10, v01, v11, xa0, xa1, ya0, ya1};
+    TsCell C;
+    C.rho = sd[b]; C.en = se[b];
+    C.u00 = su[b]; C.u10 = su[b + 1]; C.u01 = su[b + TT_BW]; C.u11 = su[b + TT_BW + 1];
+    C.v00 = sv[b]; C.v10 = sv[b + 1]; C.v01 = sv[b + TT_BW]; C.v11 = sv[b + TT_BW + 1];
+    C.vol = svol[b];
+    C.xa0 = sxa[b]; C.xa1 = sxa[b + 1]; C.ya0 = sya[b]; C.ya1 = sya[b + TT_BW];
+    C.dsx = dsx; C.dsy = dsy; C.dsx1 = dsx1; C.dsy1 = dsy1;
     if (active) {
       bool bad = false;
       double p, ss, q;
-      double cell_dt = timestep_cell<false>(rho, en, V, D, P, p, ss, q, bad);
-      if (bad) cell_dt = timestep_cell<true>(rho, en, V, D, P, p, ss, q, bad);
+      const unsigned mask = __activemask();
+      double cell_dt = timestep_cell_lean<false>(C, sd, se, b, TT_BW, P, mask, p, ss, q, bad);
+      if (bad) cell_dt = timestep_cell_lean<true>(C, sd, se, b, TT_BW, P, mask, p, ss, q, bad);
       const size_t c = idx2(pitch, j, k);
       pressure[c] = p;
       viscosity[c] = q;
       if (WRITE_SS) soundspeed[c] = ss;
       if (cell_dt < m[0]) m[0] = cell_dt;
-      // depth-1 halo ring of pressure (corners by the corner cells)
+      // depth-1 halo ring of pressure (corners by the corner cells): ideal_gas_kernel_c.c:52 for the neighbour cell
       const bool L = (j == 1), R_ = (j == nx), B = (k == 1), T = (k == ny);
-      if (L) pressure[c - 1] = pl;
-      if (R_) pressure[c + 1] = pr;
-      if (B) pressure[c - pitch] = pb;
-      if (T) pressure[c + pitch] = pt;
-      if ((L || R_) && (B || T)) {
-        const size_t cc = c + (L ? -1 : 1) + (B ? -(ptrdiff_t)pitch : (ptrdiff_t)pitch);
-        pressure[cc] = (1.4 - 1.0) * density0[cc] * energy0[cc];
-        // a one-cell-wide or one-cell-high chunk: the same cell is on both rims
-        if (L && R_) { const size_t c2 = c + 1 + (B ? -(ptrdiff_t)pitch : (ptrdiff_t)pitch); pressure[c2] = (1.4 - 1.0) * density0[c2] * energy0[c2]; }
-        if (B && T) { const size_t c2 = c + (L ? -1 : 1) + (ptrdiff_t)pitch; pressure[c2] = (1.4 - 1.0) * density0[c2] * energy0[c2]; }
-        if (L && R_ && B && T) { const size_t c2 = c + 1 + (ptrdiff_t)pitch; pressure[c2] = (1.4 - 1.0) * density0[c2] * energy0[c2]; }
+      if (L | R_ | B | T) {
+        if (L) pressure[c - 1] = (1.4 - 1.0) * sd[b - 1] * se[b - 1];
+        if (R_) pressure[c + 1] = (1.4 - 1.0) * sd[b + 1] * se[b + 1];
+        if (B) pressure[c - pitch] = (1.4 - 1.0) * sd[b - TT_BW] * se[b - TT_BW];
+        if (T) pressure[c + pitch] = (1.4 - 1.0) * sd[b + TT_BW] * se[b + TT_BW];
+        if ((L || R_) && (B || T)) {
+          const size_t cc = c + (L ? -1 : 1) + (B ? -(ptrdiff_t)pitch : (ptrdiff_t)pitch);
+          pressure[cc] = (1.4 - 1.0) * density0[cc] * energy0[cc];
+          // a one-cell-wide or one-cell-high chunk: the same cell is on both rims
+          if (L && R_) { const size_t c2 = c + 1 + (B ? -(ptrdiff_t)pitch : (ptrdiff_t)pitch); pressure[c2] = (1.4 - 1.0) * density0[c2] * energy0[c2]; }
+          if (B && T) { const size_t c2 = c + (L ? -1 : 1) + (ptrdiff_t)pitch; pressure[c2] = (1.4 - 1.0) * density0[c2] * energy0[c2]; }
+          if (L && R_ && B && T) { const size_t c2 = c + 1 + (ptrdiff_t)pitch; pressure[c2] = (1.4 - 1.0) * density0[c2] * energy0[c2]; }
+        }
       }
     }
+    __syncthreads();  // the stage (read on demand above: neighbour pressures of compressing / rim cells) can be refilled
   }
   gate.finish();
   block_reduce_publish<1, true>(m, partials, ticket, out, P.g_big, RT);
@@ -823,7 +846,11 @@ static size_t fuse_timestep(const Op* q, size_t n, size_t i) {
     const double* e0 = dev(g, energy0, CELL, IN);
     double* p = dev(g, pressure, CELL, OUT_FULL);
     double* qv = dev(g, viscosity, CELL, OUT_FULL);
+    // the sound speed is consumed on chip; in resident mode the array is only marked "c(density0, energy0), not
+    // evaluated yet" (runtime.cu: lazy_soundspeed) -- one store pass less
+    const bool lazy_ss = is_resident() && tma_enabled();
     double* ss = dev(g, soundspeed, CELL, OUT_FULL);
+    if (lazy_ss) lazy_soundspeed(g, soundspeed, density0, energy0);
     const double* xv = dev(g, xvel0, VERTEX, IN);
     const double* yv = dev(g, yvel0, VERTEX, IN);
     const DtParams P{dt.sv[0], dt.sv[1], dt.sv[2], dt.sv[3], dt.sv[4], dt.sv[5]};
@@ -839,6 +866,7 @@ static size_t fuse_timestep(const Op* q, size_t n, size_t i) {
       static bool configured = false;
       if (!configured) {
         CLV_CUDA(cudaFuncSetAttribute(timestep_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM));
+        CLV_CUDA(cudaFuncSetAttribute(timestep_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM));
         configured = true;
       }
       TimestepMaps M;
@@ -851,9 +879,9 @@ static size_t fuse_timestep(const Op* q, size_t n, size_t i) {
       double* part = partials((size_t)ctas);
       LaunchScope ls("timestep_tma");
       const TileOrder ord = tile_order_split(ntx, nty, TT_W, TT_H, 2, TT_BW - 2 - TT_W, 1, TT_BH - 1 - TT_H, g.nx, g.ny);
-      launch_pdl(timestep_tma_kernel<true>, dim3(ctas), dim3(BX, BY), TT_SMEM, stream(), M, P, cdx, cdy, d0, e0, p, qv, ss, part,
-                 ticket(), host_scalars(), g.nx, g.ny, g.pitch, ntx, ntiles, ord.table, next_tickets(ntiles, ctas), dep_start_for(ord),
-                 ls.trace, RT);
+      launch_pdl(lazy_ss ? timestep_tma_kernel<false> : timestep_tma_kernel<true>, dim3(ctas), dim3(BX, BY), TT_SMEM, stream(), M,
+                 P, cdx, cdy, d0, e0, p, qv, ss, part, ticket(), host_scalars(), g.nx, g.ny, g.pitch, ntx, ntiles, ord.table,
+                 next_tickets(ntiles, ctas), dep_start_for(ord), ls.trace, RT);
     } else {
     const dim3 grid = persistent_grid(r, 1, g_ctas_per_sm_timestep[0]);
     double* part = partials((size_t)grid.x * grid.y);
@@ -906,7 +934,9 @@ static size_t fuse_predict(const Op* q, size_t n, size_t i) {
     const double* e0 = dev(g, energy0, CELL, IN);
     double* p = dev(g, pressure, CELL, INOUT);
     const double* qv = dev(g, viscosity, CELL, IN);
-    double* ss = dev(g, soundspeed, CELL, OUT);
+    // written in full, or dead (overwritten later in this stretch before anything reads it): either way a pending
+    // lazy evaluation of the sound speed (fuse_timestep) is superseded
+    double* ss = dev(g, soundspeed, CELL, OUT_FULL);
     const double* x0 = dev(g, xvel0, VERTEX, IN);
     const double* y0 = dev(g, yvel0, VERTEX, IN);
     if (tma_enabled()) {

@@ -263,4 +263,48 @@ __device__ __forceinline__ double calc_dt_cell(const DtIn& I, const DtParams& P,
   return dmin(dtct, dmin(dtut, dmin(dtvt, dtdivt)));
 }
 
+// The same minimum as calc_dt_cell, evaluated with fewer divisions (the fused timestep launch is issue-bound, not
+// bandwidth-bound: profiles/).  Bit-identical by construction:
+//   * 2q/rho is +-0 when q == 0 (rho is normal: ideal_gas's 1/rho has already flagged anything else), and cc + (+-0)
+//     == cc for cc = c*c >= +0: the division is skipped when no lane of the warp has a non-zero viscosity;
+//   * dtu = numu/denu only matters if it is the minimum.  If numu > dtct*denu*(1+1e-6) then the correctly rounded
+//     quotient is >= dtct (two roundings of 2^-53 against a margin of 1e-6), so min(dtct, dtu, ..) == min(dtct, ..):
+//     the division is skipped (dtu := g_big; the result never exceeds g_big because dtdiv <= g_big) unless some lane
+//     of the warp cannot rule it out.  Same for dtv.  NaNs fail the test and take the division.
+//   * div/(2 vol) >= 0 whenever div >= 0 (vol > 0), i.e. "not compressing": dtdiv = g_big without dividing.
+// Lanes that do not need a division but sit in a warp that does simply compute it (same value as before).
+template <bool SAFE>
+__device__ __forceinline__ double calc_dt_cell_lean(const DtIn& I, const DtParams& P, bool& bad, unsigned mask) {
+  typedef Math<SAFE> M;
+  // (the generic re-run -- SAFE, only the lanes whose fast path flagged an operand -- does not vote: it divides)
+  auto any = [&](bool pred) { return SAFE ? true : (__any_sync(mask, pred) != 0); };
+  double cc = I.ssp * I.ssp;
+  if (any(I.visc != 0.0)) cc = cc + M::div(2.0 * I.visc, I.rho, bad);
+  cc = dmax(M::sqrt(cc, bad), P.g_small);
+  const double dtct = M::div(P.dtc_safe * dmin(I.dsx, I.dsy), cc, bad);
+  double div = 0.0;
+  double dv1 = (I.u00 + I.u01) * I.xa0;
+  double dv2 = (I.u10 + I.u11) * I.xa1;
+  div = div + dv2 - dv1;
+  const double numu = P.dtu_safe * 2.0 * I.vol;
+  const double denu = dmax(fabs(dv1), dmax(fabs(dv2), P.g_small * I.vol));
+  dv1 = (I.v00 + I.v10) * I.ya0;
+  dv2 = (I.v01 + I.v11) * I.ya1;
+  div = div + dv2 - dv1;
+  const double numv = P.dtv_safe * 2.0 * I.vol;
+  const double denv = dmax(fabs(dv1), dmax(fabs(dv2), P.g_small * I.vol));
+  const double bu = dtct * denu, bv = dtct * denv;
+  const bool need_u = !(bu >= 1.0e-280 && numu > bu * 1.000001);
+  const bool need_v = !(bv >= 1.0e-280 && numv > bv * 1.000001);
+  double dtut = P.g_big, dtvt = P.g_big, dtdivt = P.g_big;
+  if (any(need_u)) dtut = M::div(numu, denu, bad);
+  if (any(need_v)) dtvt = M::div(numv, denv, bad);
+  if (any(!(div >= 0.0))) {
+    const double dq = M::div(div, 2.0 * I.vol, bad);
+    // the divergence limit applies to compressing cells only: generic operator in that minority branch
+    dtdivt = (dq < -P.g_small) ? P.dtdiv_safe * (-1.0 / dq) : P.g_big;
+  }
+  return dmin(dtct, dmin(dtut, dmin(dtvt, dtdivt)));
+}
+
 }  // namespace clv

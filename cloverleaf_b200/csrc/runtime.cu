@@ -35,6 +35,7 @@ struct Entry {
   int nx = 0, ny = 0;
   size_t doubles = 0;
   const double* lazy_src = nullptr;  // pending lazy copy: my update range := that of lazy_src's mirror
+  const double* lazy_src2 = nullptr; // non-null: pending lazy soundspeed: my interior := c(lazy_src = density, lazy_src2 = energy)
 };
 
 struct Buffer {
@@ -286,6 +287,7 @@ static void materialize_all();
 static void drop_lazy(Entry& e) {
   if (e.lazy_src) {
     e.lazy_src = nullptr;
+    e.lazy_src2 = nullptr;
     R.lazy_pending--;
   }
 }
@@ -318,21 +320,29 @@ static Entry& lookup(const Grid& g, const double* host, Kind kind, bool* fresh) 
 
 // ---- lazy copies ----------------------------------------------------------------------------------
 void launch_copy_range(const Grid& g, const double* src, double* dst, Kind kind);  // lagrange.cu
+void launch_soundspeed(const Grid& g, const double* density, const double* energy, double* soundspeed);  // lagrange.cu
 
 static void materialize(Entry& e) {
   if (!e.lazy_src) return;
   auto it = R.arrays.find(e.lazy_src);
   if (it == R.arrays.end()) fatal("lazy copy source vanished");
   Grid g{e.nx, e.ny, pitch_for(e.nx)};
-  launch_copy_range(g, it->second.d, e.d, e.kind);
+  if (e.lazy_src2) {
+    auto i2 = R.arrays.find(e.lazy_src2);
+    if (i2 == R.arrays.end()) fatal("lazy soundspeed source vanished");
+    launch_soundspeed(g, it->second.d, i2->second.d, e.d);
+  } else {
+    launch_copy_range(g, it->second.d, e.d, e.kind);
+  }
   e.lazy_src = nullptr;
+  e.lazy_src2 = nullptr;
   R.lazy_pending--;
 }
-// `host` is about to be modified: perform every pending copy that reads from it
+// `host` is about to be modified: perform every pending copy / evaluation that reads from it
 static void materialize_dependents(const double* host) {
   if (R.lazy_pending == 0) return;
   for (auto& kv : R.arrays)
-    if (kv.second.lazy_src == host) materialize(kv.second);
+    if (kv.second.lazy_src == host || kv.second.lazy_src2 == host) materialize(kv.second);
 }
 static void materialize_all() {
   if (R.lazy_pending == 0) return;
@@ -366,6 +376,20 @@ void lazy_copy(const Grid& g, const double* dst_host, const double* src_host, Ki
   dev(g, dst_host, kind, OUT_FULL);  // exists; whatever was pending for dst is superseded; dependents of dst done
   Entry& d = R.arrays.find(dst_host)->second;
   d.lazy_src = src_host;
+  R.lazy_pending++;
+}
+
+// soundspeed := c(density, energy) on the interior (ideal_gas_kernel_c.c:48-59), recorded instead of evaluated: the
+// fused timestep launch consumes the sound speed on chip, and in the reference's call order the array is overwritten
+// (PdV predictor's ideal_gas) or dead before anything reads it.  Any read (calc_dt on its own, a download), or a
+// write to density / energy, evaluates it first; an overwrite drops it.
+void lazy_soundspeed(const Grid& g, const double* ss_host, const double* d_host, const double* e_host) {
+  dev(g, d_host, CELL, IN);
+  dev(g, e_host, CELL, IN);
+  dev(g, ss_host, CELL, OUT_FULL);
+  Entry& s = R.arrays.find(ss_host)->second;
+  s.lazy_src = d_host;
+  s.lazy_src2 = e_host;
   R.lazy_pending++;
 }
 
