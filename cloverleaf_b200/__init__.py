@@ -11,7 +11,8 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB_B200 = os.path.join(HERE, "libclover_b200.so")
+# $CLOVER_B200_LIB: another build of the same library (A/B runs of compile-time variants, profiles/); default in-tree
+LIB_B200 = os.environ.get("CLOVER_B200_LIB") or os.path.join(HERE, "libclover_b200.so")
 LIB_DRIVER = os.path.join(HERE, "libclover_driver.so")
 DECK_DIR = os.path.join(HERE, "decks")
 

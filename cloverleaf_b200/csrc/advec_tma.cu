@@ -85,25 +85,34 @@ __global__ void __launch_bounds__(TX* TY, CPS)
   const int G = gridDim.x;
   pdl_trigger();
   PdlGate gate(dep_start, trace);
+  // The halo ring of the old buffers (what the preceding halo exchange / reflective boundary delivered) moves to the
+  // new ones: up front, next to the first TMA loads, when this launch waits for its predecessor anyway; after the
+  // tiles when the interior tiles run ahead of a halo kernel (dep_start > 0).
+  if (dep_start == 0) {
+    gate.need(0);
+    ring_copy(va_old, va_new, nx, ny, pitch, 1, (int)blockIdx.x * NT + tid, G * NT);
+    ring_copy(vb_old, vb_new, nx, ny, pitch, 1, (int)blockIdx.x * NT + tid, G * NT);
+  }
   auto issue_tile = [&](int stage, int2 xy) {
     const int j0 = 1 + xy.x * W, k0 = 1 + xy.y * H;
     ring.issue(M.m, stage, j0 - OX + XOFF, k0 - OY + 1);
   };
   __shared__ int s_tile[STAGES];
   __shared__ int2 s_xy[STAGES];
-  TileQueue<STAGES> queue(tickets, ntiles, order, s_tile, s_xy);
+  __shared__ int s_q[8];
+  TileQueue<STAGES> queue(tickets, ntiles, order, s_tile, s_xy, s_q);
+  const bool sched = (tid == 32);  // lane 0 of warp 1 drives the tile queue (tma.cuh)
+  if (sched) queue.prime_all();
+  __syncthreads();
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-      int t;
-      int2 xy;
-      if (queue.draw(s, t, xy)) {
-        gate.need(t);
-        issue_tile(s, xy);
+      if (s_tile[s] < ntiles) {
+        gate.need(s_tile[s]);
+        issue_tile(s, s_xy[s]);
       }
     }
   }
-  __syncthreads();
   // the sweep axis in box / plane coordinates: moving one node along the sweep
   constexpr int SB = DIR == 1 ? 1 : BW;   // box stride along the sweep
   constexpr int SP = DIR == 1 ? 1 : TX;   // plane stride along the sweep
@@ -114,11 +123,11 @@ __global__ void __launch_bounds__(TX* TY, CPS)
     const int2 cur = s_xy[stage];
     gate.need(t);
     if (tid == 0) {
-      int tn;
-      int2 xy;
-      if (queue.draw((stage + STAGES - 1) % STAGES, tn, xy)) {
+      const int ns = (stage + STAGES - 1) % STAGES;
+      const int tn = s_tile[ns];
+      if (tn < ntiles) {
         gate.need(tn);
-        issue_tile((stage + STAGES - 1) % STAGES, xy);
+        issue_tile(ns, s_xy[ns]);
       }
     }
     const int j0 = 1 + cur.x * W, k0 = 1 + cur.y * H;
@@ -188,6 +197,7 @@ __global__ void __launch_bounds__(TX* TY, CPS)
       }
     }
     __syncthreads();
+    if (sched) queue.step(stage);  // everybody has read this iteration's table slot
     // ---- B: mom_flux at sweep positions 1 .. NPS-3 ---------------------------------------------------------------------
     double ma[RPT], mb[RPT], va0[RPT], vb0[RPT], nm_pre[RPT];
 #pragma unroll
@@ -236,10 +246,12 @@ __global__ void __launch_bounds__(TX* TY, CPS)
     }
     __syncthreads();  // stage and planes are free again
   }
-  // the halo ring of the old buffers (what the preceding halo exchange / reflective boundary delivered) moves to the new ones
   gate.finish();
-  ring_copy(va_old, va_new, nx, ny, pitch, 1, (int)blockIdx.x * NT + tid, G * NT);
-  ring_copy(vb_old, vb_new, nx, ny, pitch, 1, (int)blockIdx.x * NT + tid, G * NT);
+  if (sched) queue.leave();
+  if (dep_start != 0) {
+    ring_copy(va_old, va_new, nx, ny, pitch, 1, (int)blockIdx.x * NT + tid, G * NT);
+    ring_copy(vb_old, vb_new, nx, ny, pitch, 1, (int)blockIdx.x * NT + tid, G * NT);
+  }
 }
 
 template <int DIR, int MS, int TX, int TY, int RPT, int STAGES, int CPS>
@@ -259,7 +271,7 @@ static void launch_mom(const Grid& g, const MomMaps& M, const double* va_old, do
   const TileOrder ord = tile_order_split(ntx, nty, Cfg::W, Cfg::H, Cfg::OX, Cfg::BW - Cfg::OX - Cfg::W, Cfg::OY,
                                          Cfg::BH - Cfg::OY - Cfg::H, g.nx, g.ny);
   launch_pdl(advec_mom_tma_kernel<DIR, MS, TX, TY, RPT, STAGES, CPS>, dim3(ctas), dim3(Cfg::NT), Cfg::SMEM, stream(), M, va_old,
-             va_new, vb_old, vb_new, celld, g.nx, g.ny, g.pitch, ntx, ntiles, ord.table, next_tickets(ntiles, ctas),
+             va_new, vb_old, vb_new, celld, g.nx, g.ny, g.pitch, ntx, ntiles, ord.table, next_tickets(),
              dep_start_for(ord), current_trace());
 }
 
@@ -313,25 +325,34 @@ __global__ void __launch_bounds__(TX* TY, CPS)
   const int ntiles = ntx * nty;
   pdl_trigger();
   PdlGate gate(dep_start, trace);
+  // The halo ring of the old buffers (what the preceding halo exchange / reflective boundary delivered) moves to the
+  // new ones: up front, next to the first TMA loads, when this launch waits for its predecessor anyway; after the
+  // tiles when the interior tiles run ahead of a halo kernel (dep_start > 0).
+  if (dep_start == 0) {
+    gate.need(0);
+    ring_copy(d_old, d_new, nx, ny, pitch, 0, (int)blockIdx.x * NT + tid, G * NT);
+    ring_copy(e_old, e_new, nx, ny, pitch, 0, (int)blockIdx.x * NT + tid, G * NT);
+  }
   auto issue_tile = [&](int stage, int2 xy) {
     const int j0 = 1 + xy.x * W, k0 = 1 + xy.y * H;
     ring.issue(M.m, stage, j0 - OX + XOFF, k0 - OY + 1);
   };
   __shared__ int s_tile[STAGES];
   __shared__ int2 s_xy[STAGES];
-  TileQueue<STAGES> queue(tickets, ntiles, order, s_tile, s_xy);
+  __shared__ int s_q[8];
+  TileQueue<STAGES> queue(tickets, ntiles, order, s_tile, s_xy, s_q);
+  const bool sched = (tid == 32);  // lane 0 of warp 1 drives the tile queue (tma.cuh)
+  if (sched) queue.prime_all();
+  __syncthreads();
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-      int t;
-      int2 xy;
-      if (queue.draw(s, t, xy)) {
-        gate.need(t);
-        issue_tile(s, xy);
+      if (s_tile[s] < ntiles) {
+        gate.need(s_tile[s]);
+        issue_tile(s, s_xy[s]);
       }
     }
   }
-  __syncthreads();
   constexpr int SB = DIR == 1 ? 1 : BW;  // box stride along the sweep
   constexpr int SP = DIR == 1 ? 1 : TX;  // plane stride along the sweep
   const int smax = (DIR == 1 ? nx : ny) + 2;
@@ -342,11 +363,11 @@ __global__ void __launch_bounds__(TX* TY, CPS)
     const int2 cur = s_xy[stage];
     gate.need(t);
     if (tid == 0) {
-      int tn;
-      int2 xy;
-      if (queue.draw((stage + STAGES - 1) % STAGES, tn, xy)) {
+      const int ns = (stage + STAGES - 1) % STAGES;
+      const int tn = s_tile[ns];
+      if (tn < ntiles) {
         gate.need(tn);
-        issue_tile((stage + STAGES - 1) % STAGES, xy);
+        issue_tile(ns, s_xy[ns]);
       }
     }
     const int tx_ = cur.x, ty_ = cur.y;
@@ -389,6 +410,7 @@ __global__ void __launch_bounds__(TX* TY, CPS)
       s_pv[p0 + r * TX] = pv[r];
     }
     __syncthreads();
+    if (sched) queue.step(stage);  // everybody has read this iteration's table slot
     // ---- B: fluxes through the lower face of position ps (valid for ps >= 1) --------------------------------------------
     double mf[RPT], ef[RPT], vf[RPT], d0[RPT], e0[RPT];
 #pragma unroll
@@ -440,10 +462,12 @@ __global__ void __launch_bounds__(TX* TY, CPS)
     }
     __syncthreads();  // stage and planes are free again
   }
-  // the halo ring of the old buffers (what the preceding halo exchange / reflective boundary delivered) moves to the new ones
   gate.finish();
-  ring_copy(d_old, d_new, nx, ny, pitch, 0, (int)blockIdx.x * NT + tid, G * NT);
-  ring_copy(e_old, e_new, nx, ny, pitch, 0, (int)blockIdx.x * NT + tid, G * NT);
+  if (sched) queue.leave();
+  if (dep_start != 0) {
+    ring_copy(d_old, d_new, nx, ny, pitch, 0, (int)blockIdx.x * NT + tid, G * NT);
+    ring_copy(e_old, e_new, nx, ny, pitch, 0, (int)blockIdx.x * NT + tid, G * NT);
+  }
 }
 
 template <int DIR, int SWEEP, int TX, int TY, int RPT, int STAGES, int CPS>
@@ -463,7 +487,7 @@ static void launch_cell(const Grid& g, const CellMaps& M, const double* d_old, d
   const TileOrder ord = tile_order_split(ntx, nty, Cfg::W, Cfg::H, Cfg::OX, Cfg::BW - Cfg::OX - Cfg::W, Cfg::OY,
                                          Cfg::BH - Cfg::OY - Cfg::H, g.nx, g.ny);
   launch_pdl(advec_cell_tma_kernel<DIR, SWEEP, TX, TY, RPT, STAGES, CPS>, dim3(ctas), dim3(Cfg::NT), Cfg::SMEM, stream(), M, d_old,
-             d_new, e_old, e_new, mass_flux, vertexd, g.nx, g.ny, g.pitch, ntx, nty, ord.table, next_tickets(ntiles, ctas),
+             d_new, e_old, e_new, mass_flux, vertexd, g.nx, g.ny, g.pitch, ntx, nty, ord.table, next_tickets(),
              dep_start_for(ord), current_trace());
 }
 

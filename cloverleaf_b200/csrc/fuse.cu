@@ -176,31 +176,35 @@ __global__ void __launch_bounds__(BX* BY, TT_CPS)
   };
   __shared__ int s_tile[TT_STAGES];
   __shared__ int2 s_xy[TT_STAGES];
-  TileQueue<TT_STAGES> queue(tickets, ntiles, order, s_tile, s_xy);
+  __shared__ int s_q[8];
+  TileQueue<TT_STAGES> queue(tickets, ntiles, order, s_tile, s_xy, s_q);
+  const bool sched = (lx == 0 && ly == 1);  // lane 0 of warp 1 drives the tile queue (tma.cuh)
+  if (sched) queue.prime_all();
+  __syncthreads();
   if (leader) {
 #pragma unroll
     for (int s = 0; s < TT_STAGES - 1; ++s) {
-      int t;
-      int2 xy;
-      if (queue.draw(s, t, xy)) {
-        gate.need(t);
-        issue_tile(s, xy);
+      if (s_tile[s] < ntiles) {
+        gate.need(s_tile[s]);
+        issue_tile(s, s_xy[s]);
       }
     }
   }
-  __syncthreads();
-  for (int it = 0;; ++it) {
+  // this iteration's tile sits in registers: it was read from the ring's table during the previous iteration (slot
+  // stage+1 is written STAGES-2 >= 2 iterations before it is due, behind at least one barrier)
+  int t = s_tile[0];
+  int2 cur = s_xy[0];
+  __syncthreads();  // slot 0 has been read: the scheduler may refill it
+  for (int it = 0; t < ntiles; ++it) {
     const int stage = it % TT_STAGES;
-    const int t = s_tile[stage];
-    if (t >= ntiles) break;
-    const int2 cur = s_xy[stage];
+    if (sched) queue.step(stage);
     gate.need(t);  // rim tiles wait for the halo kernel (their loads, issued STAGES-1 tiles ahead, waited in the leader)
     if (leader) {
-      int tn;
-      int2 xy;
-      if (queue.draw((stage + TT_STAGES - 1) % TT_STAGES, tn, xy)) {
+      const int ns = (stage + TT_STAGES - 1) % TT_STAGES;
+      const int tn = s_tile[ns];
+      if (tn < ntiles) {
         gate.need(tn);
-        issue_tile((stage + TT_STAGES - 1) % TT_STAGES, xy);
+        issue_tile(ns, s_xy[ns]);
       }
     }
     const int j = 1 + cur.x * TT_W + lx, k = 1 + cur.y * TT_H + ly;
@@ -208,6 +212,8 @@ __global__ void __launch_bounds__(BX* BY, TT_CPS)
     const int jc = j <= nx ? j : nx, kc = k <= ny ? k : ny;  // 1-D geometry of the threads beyond the chunk
     const double dsx = celldx[jc + 1], dsy = celldy[kc + 1], dsx1 = celldx[jc + 2], dsy1 = celldy[kc + 2];
     ring.wait(stage, (uint32_t)((it / TT_STAGES) & 1));
+    const int t_nx = s_tile[(stage + 1) % TT_STAGES];
+    const int2 xy_nx = s_xy[(stage + 1) % TT_STAGES];
     const double* __restrict__ sd = ring.tile(stage, TA_D0);
     const double* __restrict__ se = ring.tile(stage, TA_E0);
     const double* __restrict__ su = ring.tile(stage, TA_U0);
@@ -252,8 +258,11 @@ __global__ void __launch_bounds__(BX* BY, TT_CPS)
       }
     }
     __syncthreads();  // the stage (read on demand above: neighbour pressures of compressing / rim cells) can be refilled
+    t = t_nx;
+    cur = xy_nx;
   }
   gate.finish();
+  if (sched) queue.leave();
   block_reduce_publish<1, true>(m, partials, ticket, out, P.g_big, RT);
 }
 
@@ -338,35 +347,41 @@ __global__ void __launch_bounds__(BX* BY, PT_CPS)
   };
   __shared__ int s_tile[PT_STAGES];
   __shared__ int2 s_xy[PT_STAGES];
-  TileQueue<PT_STAGES> queue(tickets, ntiles, order, s_tile, s_xy);
+  __shared__ int s_q[8];
+  TileQueue<PT_STAGES> queue(tickets, ntiles, order, s_tile, s_xy, s_q);
+  const bool sched = (lx == 0 && ly == 1);  // lane 0 of warp 1 drives the tile queue (tma.cuh)
+  if (sched) queue.prime_all();
+  __syncthreads();
   if (leader) {
 #pragma unroll
     for (int s = 0; s < PT_STAGES - 1; ++s) {
-      int t;
-      int2 xy;
-      if (queue.draw(s, t, xy)) {
-        gate.need(t);
-        issue_tile(s, xy);
+      if (s_tile[s] < ntiles) {
+        gate.need(s_tile[s]);
+        issue_tile(s, s_xy[s]);
       }
     }
   }
-  __syncthreads();
-  for (int it = 0;; ++it) {
+  // this iteration's tile sits in registers: it was read from the ring's table during the previous iteration (slot
+  // stage+1 is written STAGES-2 >= 2 iterations before it is due, behind at least one barrier)
+  int t = s_tile[0];
+  int2 cur = s_xy[0];
+  __syncthreads();  // slot 0 has been read: the scheduler may refill it
+  for (int it = 0; t < ntiles; ++it) {
     const int stage = it % PT_STAGES;
-    const int t = s_tile[stage];
-    if (t >= ntiles) break;
-    const int2 cur = s_xy[stage];
+    if (sched) queue.step(stage);
     gate.need(t);
     if (leader) {
-      int tn;
-      int2 xy;
-      if (queue.draw((stage + PT_STAGES - 1) % PT_STAGES, tn, xy)) {
+      const int ns = (stage + PT_STAGES - 1) % PT_STAGES;
+      const int tn = s_tile[ns];
+      if (tn < ntiles) {
         gate.need(tn);
-        issue_tile((stage + PT_STAGES - 1) % PT_STAGES, xy);
+        issue_tile(ns, s_xy[ns]);
       }
     }
     const int j = 1 + cur.x * PT_W + lx, k = 1 + cur.y * PT_H + ly;
     ring.wait(stage, (uint32_t)((it / PT_STAGES) & 1));
+    const int t_nx = s_tile[(stage + 1) % PT_STAGES];
+    const int2 xy_nx = s_xy[(stage + 1) % PT_STAGES];
     const double* __restrict__ sxa = ring.tile(stage, PA_XAREA);
     const double* __restrict__ sya = ring.tile(stage, PA_YAREA);
     const double* __restrict__ sx = ring.tile(stage, PA_XVEL0);
@@ -399,8 +414,11 @@ __global__ void __launch_bounds__(BX* BY, PT_CPS)
       pressure[c] = p;
       if (WRITE_SS) soundspeed[c] = ss;
     }
+    t = t_nx;
+    cur = xy_nx;
   }
   gate.finish();
+  if (sched) queue.leave();
 }
 
 // ================================================================================================
@@ -559,19 +577,20 @@ __global__ void __launch_bounds__(W* LT_H / RPT, CPS)
   };
   __shared__ int s_tile[STAGES];
   __shared__ int2 s_xy[STAGES];
-  TileQueue<STAGES> queue(tickets, ntiles, order, s_tile, s_xy);
+  __shared__ int s_q[8];
+  TileQueue<STAGES> queue(tickets, ntiles, order, s_tile, s_xy, s_q);
+  const bool sched = (tid == 32);  // lane 0 of warp 1 drives the tile queue (tma.cuh)
+  if (sched) queue.prime_all();
+  __syncthreads();
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-      int t;
-      int2 xy;
-      if (queue.draw(s, t, xy)) {
-        gate.need(t);
-        issue_tile(s, xy);
+      if (s_tile[s] < ntiles) {
+        gate.need(s_tile[s]);
+        issue_tile(s, s_xy[s]);
       }
     }
   }
-  __syncthreads();
   for (int it = 0;; ++it) {
     const int stage = it % STAGES;
     const int t = s_tile[stage];
@@ -579,11 +598,11 @@ __global__ void __launch_bounds__(W* LT_H / RPT, CPS)
     const int2 cur = s_xy[stage];
     gate.need(t);
     if (tid == 0) {  // the stage it refills was released by the barrier that ended iteration it-1
-      int tn;
-      int2 xy;
-      if (queue.draw((stage + STAGES - 1) % STAGES, tn, xy)) {
+      const int ns = (stage + STAGES - 1) % STAGES;
+      const int tn = s_tile[ns];
+      if (tn < ntiles) {
         gate.need(tn);
-        issue_tile((stage + STAGES - 1) % STAGES, xy);
+        issue_tile(ns, s_xy[ns]);
       }
     }
     const int j0 = 1 + cur.x * LT_W, k0 = 1 + cur.y * LT_H;
@@ -637,6 +656,7 @@ __global__ void __launch_bounds__(W* LT_H / RPT, CPS)
       }
     }
     __syncthreads();
+    if (sched) queue.step(stage);  // (everybody has read this iteration's table slot; the leader reads the new entry after the next barrier)
     // ---- phase 2: faces (flux_calc_kernel_c.c:55-58, :67-70) and cells (PdV_kernel_c.c:117-163) ------------------
     {
       double fx[RPT], fy[RPT], e1[RPT], d1[RPT];
@@ -682,6 +702,7 @@ __global__ void __launch_bounds__(W* LT_H / RPT, CPS)
     __syncthreads();  // stage and su1/sv1 are free again
   }
   gate.finish();
+  if (sched) queue.leave();
 }
 
 template <int W, int RPT, int STAGES, int CPS>
@@ -704,7 +725,7 @@ static void launch_correct_tma(const CorrectArgs& A, const Grid& g, double dt) {
   const int ctas = ntiles < cap ? ntiles : cap;
   const TileOrder ord = tile_order_split(ntx, nty, LT_W, LT_H, LT_OX, Cfg::BW - LT_OX - LT_W, 1, LT_BH - 1 - LT_H, g.nx, g.ny);
   launch_pdl(lagrange_correct_tma_kernel<W, RPT, STAGES, CPS>, dim3(ctas), dim3(Cfg::NT), Cfg::SMEM, stream(), M, O, g.nx, g.ny,
-             g.pitch, dt, ntx, ntiles, ord.table, next_tickets(ntiles, ctas), dep_start_for(ord), current_trace());
+             g.pitch, dt, ntx, ntiles, ord.table, next_tickets(), dep_start_for(ord), current_trace());
 }
 
 // single-call host launchers (lagrange.cu, advec.cu)
@@ -881,7 +902,7 @@ static size_t fuse_timestep(const Op* q, size_t n, size_t i) {
       const TileOrder ord = tile_order_split(ntx, nty, TT_W, TT_H, 2, TT_BW - 2 - TT_W, 1, TT_BH - 1 - TT_H, g.nx, g.ny);
       launch_pdl(lazy_ss ? timestep_tma_kernel<false> : timestep_tma_kernel<true>, dim3(ctas), dim3(BX, BY), TT_SMEM, stream(), M,
                  P, cdx, cdy, d0, e0, p, qv, ss, part, ticket(), host_scalars(), g.nx, g.ny, g.pitch, ntx, ntiles, ord.table,
-                 next_tickets(ntiles, ctas), dep_start_for(ord), ls.trace, RT);
+                 next_tickets(), dep_start_for(ord), ls.trace, RT);
     } else {
     const dim3 grid = persistent_grid(r, 1, g_ctas_per_sm_timestep[0]);
     double* part = partials((size_t)grid.x * grid.y);
@@ -956,7 +977,7 @@ static size_t fuse_predict(const Op* q, size_t n, size_t i) {
       LaunchScope ls("pdv_predict_tma");
       const TileOrder ord = tile_order_split(ntx, nty, PT_W, PT_H, 0, PT_BW - PT_W, 0, PT_BH - PT_H, g.nx, g.ny);
       const int dep = dep_start_for(ord);
-      const Tickets tk = next_tickets(ntiles, ctas);
+      const Tickets tk = next_tickets();
       if (write_ss)
         launch_pdl(pdv_predict_eos_tma_kernel<true>, dim3(ctas), dim3(BX, BY), PT_SMEM, stream(), M, pv.sv[0], p, ss, g.nx, g.ny,
                    g.pitch, ntx, ntiles, ord.table, tk, dep, ls.trace);

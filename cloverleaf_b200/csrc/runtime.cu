@@ -78,7 +78,7 @@ struct Runtime {
   bool pdl = true;        // programmatic dependent launch ($CLOVER_B200_PDL=0 disables)
   bool split = true;      // interior tiles before the halo wait ($CLOVER_B200_SPLIT=0: wait before the first tile)
   bool halo_noted = false;  // the last launch was an exchange / update_halo kernel
-  unsigned int ticket_issued[4] = {0, 0, 0, 0};
+  unsigned int* d_tickets = nullptr;  // ring of {tickets, exits} pairs (next_tickets)
   unsigned int ticket_turn = 0;
   bool trace_on = false;                 // in-situ timeline (clover_b200_trace_)
   unsigned long long* d_trace = nullptr;  // 4 stamps per launch
@@ -665,15 +665,23 @@ TileOrder tile_order_split(int ntx, int nty, int tw, int th, int lo_x, int hi_x,
   return o;
 }
 
-// Ticket counters of the dynamic tile queues (tma.cuh): four device counters used in turn (at most two consecutive
-// launches ever draw at the same time: a dependent's CTAs start while its predecessor's last CTAs are finishing),
-// never reset; the host mirrors their values (uint32 arithmetic wraps consistently on both sides).
-Tickets next_tickets(int ntiles, int ctas) {
-  const int i = R.ticket_turn++ & 3;
+// Ticket counters of the dynamic tile queues (tma.cuh): a ring of zero-initialised {tickets, exits} pairs, one pair
+// per launch; the launch itself zeroes its pair when its last CTA leaves.  The ring is far longer than the number of
+// grids that can be in flight at once (a PDL chain of tiny kernels can have many resident at the same time).
+constexpr unsigned int TICKET_RING = 2048;
+Tickets next_tickets() {
+  static int dynamic = -1;
+  if (dynamic < 0) {
+    const char* e = getenv("CLOVER_B200_QUEUE");
+    dynamic = (e && strcmp(e, "static") == 0) ? 0 : 1;
+  }
+  if (!dynamic) return Tickets{nullptr};
+  if (!R.d_tickets) {
+    CLV_CUDA(cudaMalloc(&R.d_tickets, TICKET_RING * 2 * sizeof(unsigned int)));
+    CLV_CUDA(cudaMemsetAsync(R.d_tickets, 0, TICKET_RING * 2 * sizeof(unsigned int), R.stream));
+  }
   Tickets t;
-  t.counter = R.d_ticket + 8 + i;
-  t.base = R.ticket_issued[i];
-  R.ticket_issued[i] += (unsigned int)ntiles + (unsigned int)ctas;
+  t.ctr = R.d_tickets + 2 * (R.ticket_turn++ % TICKET_RING);
   return t;
 }
 
@@ -719,7 +727,6 @@ void clover_b200_init_(int* device) {
   CLV_CUDA(cudaHostAlloc(&R.h_scalars, 64 * sizeof(double), cudaHostAllocMapped));
   CLV_CUDA(cudaMalloc(&R.d_ticket, 16 * sizeof(unsigned int)));
   CLV_CUDA(cudaMemset(R.d_ticket, 0, 16 * sizeof(unsigned int)));
-  for (int i = 0; i < 4; ++i) R.ticket_issued[i] = 0;
   R.ticket_turn = 0;
   CLV_CUDA(cudaEventCreate(&R.ev0));
   CLV_CUDA(cudaEventCreate(&R.ev1));
@@ -746,6 +753,8 @@ void clover_b200_finalize_(void) {
   R.d_partials = nullptr;
   R.partials_doubles = 0;
   CLV_CUDA(cudaFree(R.d_ticket));
+  if (R.d_tickets) CLV_CUDA(cudaFree(R.d_tickets));
+  R.d_tickets = nullptr;
   CLV_CUDA(cudaFreeHost(R.h_scalars));
   R.h_scalars = nullptr;
   CLV_CUDA(cudaEventDestroy(R.ev0));

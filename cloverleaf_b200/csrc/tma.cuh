@@ -128,45 +128,113 @@ struct TileRing {
   __device__ __forceinline__ void wait(int stage, uint32_t parity) { mbar_wait(&full[stage], parity); }
 };
 
-// Dynamic tile scheduling for the persistent kernels: CTAs draw tickets from a device counter (one atomicAdd per
-// tile, by the CTA's leader, STAGES-1 tiles ahead of the tile being computed) instead of striding through the table.
-// Why: (1) CTAs that become resident late -- their SM slot was still held by the halo-exchange kernel they overlap
-// with (PDL) or by the tail of the previous kernel -- simply take fewer tiles instead of finishing late with a full
-// static share; (2) data-dependent tile costs (the zero-numerator / inactive-limiter short cuts) balance out.
-// The counter is never reset: the host passes `base` = its value before this launch; every CTA draws exactly one
-// ticket past the end, so a launch advances it by ntiles + gridDim.x (runtime.cu: next_tickets).  Tickets follow the
-// order table, so interior tiles still come first and tiles in flight at the same time are still neighbours.
+// Dynamic tile scheduling for the persistent kernels: CTAs draw tickets from a device counter instead of striding
+// through the order table.  Why: (1) CTAs that become resident late -- their SM slot was still held by the
+// halo-exchange kernel they overlap with (PDL) or by the tail of the previous kernel -- simply take fewer tiles instead
+// of finishing late with a full static share; (2) data-dependent tile costs (the zero-numerator / inactive-limiter
+// short cuts) balance out.  Tickets follow the order table, so interior tiles still come first and the tiles in
+// flight at any moment are still neighbours (L2 reuse of shared halo rows).
+// The CTA's leader keeps the latencies off the critical path: at iteration i it issues the TMA loads of a tile whose
+// table entry it asked for at i-1 and whose chunk of tickets it drew at least one chunk earlier (an atomicAdd or a
+// table load consumed in the iteration that issues it cost ~1 us per tile: measured +50 % on pdv_predict).
+// Every launch has its own counter pair {tickets, exits} from a ring (runtime.cu: next_tickets); the last CTA to
+// leave zeroes the pair for its next use, so no host-side arithmetic depends on how many tickets were drawn.
 struct Tickets {
-  unsigned int* counter;
-  unsigned int base;
+  unsigned int* ctr;  // [0] next ticket, [1] CTAs that have left; nullptr: static schedule (A/B switch)
 };
+// Tickets are drawn QCHUNK at a time: one atomicAdd per tile (57 600 tiles of 32x8 cells at 3840^2, 296 CTAs asking every
+// ~1 us) saturates the single L2 address and its queueing latency lands on the leader's critical path (measured:
+// pdv_predict 0.225 -> 0.288 ms).  A chunk is also a run of horizontally adjacent tiles, which share halo columns.
+#ifndef QCHUNK
+#define QCHUNK 4
+#endif
 template <int STAGES>
 struct TileQueue {
-  Tickets tk;
+  unsigned int* ctr;
   int ntiles;
   const int2* order;
-  bool exhausted;
   int* s_tile;   // [STAGES] shared: tile index loaded into each ring stage (>= ntiles: none)
   int2* s_xy;    // [STAGES] shared: its coordinates
-  __device__ __forceinline__ TileQueue(Tickets t, int n, const int2* o, int* st, int2* sx)
-      : tk(t), ntiles(n), order(o), exhausted(false), s_tile(st), s_xy(sx) {}
-  // leader only: draw the next ticket for ring slot `slot`; true (+ index, coordinates) if it is a tile
-  __device__ __forceinline__ bool draw(int slot, int& t, int2& xy) {
-    t = ntiles;
-    if (!exhausted) {
-      const unsigned int v = atomicAdd(tk.counter, 1u) - tk.base;
-      if (v < (unsigned int)ntiles) t = (int)v;
-      else exhausted = true;
+  // The leader's look-ahead state lives in shared memory too (s_q, 8 words): registers are allocated for every thread
+  // of the kernel, and the advection kernels run at 80 registers (3 CTAs/SM) where six more meant spills in the tile
+  // loop.  s_q: [0] t_look, [3] cur_lo, [4] cur_hi, [6] turn (static schedule).  What is still in flight when an
+  // iteration ends -- the raw return value of the chunk atomic and the table entry of the look-ahead tile -- stays in
+  // registers: a store of either would park the leader's warp (in-order issue) for the whole L2 round trip.
+  int* s_q;
+  unsigned int nxt_raw;  // first ticket of the next chunk: its atomicAdd is in flight / here
+  int2 xy_look;          // coordinates of tile t_look: its table load is in flight / here
+  __device__ __forceinline__ TileQueue(Tickets t, int n, const int2* o, int* st, int2* sx, int* sq)
+      : ctr(t.ctr), ntiles(n), order(o), s_tile(st), s_xy(sx), s_q(sq), nxt_raw((unsigned int)n), xy_look(make_int2(0, 0)) {}
+  __device__ __forceinline__ int clampt(unsigned int v) const { return v < (unsigned int)ntiles ? (int)v : ntiles; }
+  // The value an atomicAdd returns is NOT touched here (warps issue in order: a compare right behind the atomic would
+  // park the leader's warp for the whole L2 round trip); it is stored, and clamped when the chunk becomes current.
+  __device__ __forceinline__ unsigned int draw_chunk() {
+    if (ctr == nullptr) return (blockIdx.x + (unsigned int)(s_q[6]++) * gridDim.x) * QCHUNK;  // CTA b: chunks b, b+G, ...
+    return atomicAdd(ctr, (unsigned int)QCHUNK);
+  }
+  __device__ __forceinline__ int pop() {
+    int lo = s_q[3];
+    const int hi = s_q[4];
+    if (lo >= hi) {  // the chunk drawn QCHUNK tiles ago becomes current, the next one is asked for now
+      lo = clampt(nxt_raw);
+      s_q[4] = min(lo + QCHUNK, ntiles);
+      if (lo < ntiles) nxt_raw = draw_chunk();  // nothing more to draw after the first miss
+      if (lo >= ntiles) { s_q[3] = lo; return ntiles; }
     }
-    s_tile[slot] = t;
-    if (t >= ntiles) return false;
-    xy = __ldg(order + t);
-    s_xy[slot] = xy;
-    return true;
+    s_q[3] = lo + 1;
+    return lo;
+  }
+  // The queue is driven by ONE thread that is not the TMA leader (the "scheduler", lane 0 of warp 1): its bookkeeping
+  // -- a dependent chain of ~50 single-thread instructions per tile -- then runs next to the leader's fence + nine
+  // UTMALDG issues instead of in front of them (in the leader it cost pdv_predict 12 %).  Protocol, per iteration i
+  // (ring stage i % STAGES is being computed):
+  //   scheduler  step(i % STAGES): table slot i % STAGES := the tile whose loads the leader issues at iteration i+1
+  //              (it is computed at iteration i+STAGES); then draws / looks up the tile after that
+  //   leader     reads slot (i + STAGES-1) % STAGES -- written by the scheduler during iteration i-1 -- and issues it
+  // with a barrier between each write and its reads (every tile loop has one per iteration).
+  __device__ __forceinline__ void prime_all() {  // scheduler, once: slots 0..STAGES-1, then the look-ahead
+    s_q[6] = 0;
+    const int lo = clampt(draw_chunk());
+    s_q[3] = lo;
+    s_q[4] = min(lo + QCHUNK, ntiles);
+    if (lo < ntiles) nxt_raw = draw_chunk();
+    int t0[STAGES];
+    int2 xy0[STAGES];
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) t0[s] = pop();
+    const int tl = pop();
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) xy0[s] = t0[s] < ntiles ? __ldg(order + t0[s]) : make_int2(0, 0);
+    xy_look = tl < ntiles ? __ldg(order + tl) : make_int2(0, 0);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      s_tile[s] = t0[s];
+      s_xy[s] = xy0[s];
+    }
+    s_q[0] = tl;
+  }
+  __device__ __forceinline__ void step(int slot) {  // scheduler, every iteration
+    s_tile[slot] = s_q[0];
+    s_xy[slot] = xy_look;  // its table load was issued an iteration ago
+    const int tl = pop();
+    xy_look = tl < ntiles ? __ldg(order + tl) : make_int2(0, 0);
+    s_q[0] = tl;
+  }
+  // scheduler, after the tile loop: all my draws have returned (the last value is compared here), so the exit count
+  // orders after them; the last CTA out re-arms the pair
+  __device__ __forceinline__ void leave() {
+    if (ctr == nullptr) return;
+    if (nxt_raw == 0xffffffffu && s_q[0] < 0) s_tile[0] = (int)nxt_raw;  // never true: waits for the last draw to return
+    __threadfence();
+    if (atomicAdd(ctr + 1, 1u) == gridDim.x - 1) {
+      ctr[0] = 0;
+      ctr[1] = 0;
+      __threadfence();
+    }
   }
 };
-// Host: ticket counter + base for a launch of `ctas` persistent CTAs over `ntiles` tiles (runtime.cu).
-Tickets next_tickets(int ntiles, int ctas);
+// Host: the counter pair for the next launch (runtime.cu).
+Tickets next_tickets();
 
 __device__ __forceinline__ unsigned char* align128(unsigned char* p) {
   return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 127) & ~(uintptr_t)127);
