@@ -62,12 +62,28 @@ static const struct { int x_inc, y_inc, m; double sx, sy; Kind kind; } kFieldGeo
 // (halo data received from a neighbour chunk).  Mirror rules:
 //     bottom: 1-k <- m+k         top:   ny+y_inc+k <- ny+y_inc+(1-m)-k
 //     left:   1-j <- m+j         right: nx+x_inc+j <- nx+x_inc+(1-m)-j
+// `part`: 0 = every reflected cell; 1 = only the cells whose mirror source is the chunk's own data (everything except
+// the few cells that lie beyond an external face AND in the halo rows / columns of a face that has a neighbour);
+// 2 = only those few, whose source is a halo cell delivered by the exchange.  The peer-memory exchange kernel reflects
+// part 1 while it waits for its neighbours' strips and part 2 after unpacking them.
+// Returns the source address (nullptr: nothing to do) so that callers can batch several loads before the stores.
+__device__ __forceinline__ const double* update_halo_source(const FieldDesc& F, int nx, int ny, int pitch, int depth,
+                                                            int ext_left, int ext_right, int ext_bottom, int ext_top, int t,
+                                                            int part, double*& dst, double& sign);
 __device__ __forceinline__ void update_halo_item(const FieldDesc& F, int nx, int ny, int pitch, int depth, int ext_left,
-                                                 int ext_right, int ext_bottom, int ext_top, int t) {
+                                                 int ext_right, int ext_bottom, int ext_top, int t, int part = 0) {
+  double* dst;
+  double sign;
+  const double* src = update_halo_source(F, nx, ny, pitch, depth, ext_left, ext_right, ext_bottom, ext_top, t, part, dst, sign);
+  if (src) *dst = sign * *src;
+}
+__device__ __forceinline__ const double* update_halo_source(const FieldDesc& F, int nx, int ny, int pitch, int depth,
+                                                            int ext_left, int ext_right, int ext_bottom, int ext_top, int t,
+                                                            int part, double*& dst, double& sign) {
   const int W = nx + F.x_inc + 2 * depth;  // width of the bottom/top strips (corners included)
   const int H = ny + F.y_inc;              // height of the left/right strips (corners excluded)
   const int n_bt = 2 * depth * W, n_lr = 2 * depth * H;
-  if (t >= n_bt + n_lr) return;
+  if (t >= n_bt + n_lr) return nullptr;
   int jd, kd;
   if (t < n_bt) {
     const int side = t / (depth * W), r = (t % (depth * W)) / W + 1;
@@ -79,11 +95,15 @@ __device__ __forceinline__ void update_halo_item(const FieldDesc& F, int nx, int
     kd = 1 + (u % H);
     jd = side == 0 ? 1 - r : nx + F.x_inc + r;
   }
+  const bool out_x = jd < 1 || jd > nx + F.x_inc, out_y = kd < 1 || kd > ny + F.y_inc;
   const bool refl_x = (jd < 1 && ext_left) || (jd > nx + F.x_inc && ext_right);
   const bool refl_y = (kd < 1 && ext_bottom) || (kd > ny + F.y_inc && ext_top);
-  if (!refl_x && !refl_y) return;
+  if (!refl_x && !refl_y) return nullptr;
+  // the source is a received halo cell iff the cell is outside in a direction that is NOT reflected
+  const bool from_halo = (out_x && !refl_x) || (out_y && !refl_y);
+  if ((part == 1 && from_halo) || (part == 2 && !from_halo)) return nullptr;
   int js = jd, ks = kd;
-  double sign = 1.0;
+  sign = 1.0;
   if (refl_x) {
     js = (jd < 1) ? F.m + (1 - jd) : nx + F.x_inc + (1 - F.m) - (jd - (nx + F.x_inc));
     sign = sign * F.sx;
@@ -92,7 +112,33 @@ __device__ __forceinline__ void update_halo_item(const FieldDesc& F, int nx, int
     ks = (kd < 1) ? F.m + (1 - kd) : ny + F.y_inc + (1 - F.m) - (kd - (ny + F.y_inc));
     sign = sign * F.sy;
   }
-  F.p[idx2(pitch, jd, kd)] = sign * F.p[idx2(pitch, js, ks)];
+  dst = F.p + idx2(pitch, jd, kd);
+  return F.p + idx2(pitch, js, ks);
+}
+// grid-stride reflection with XU_R independent loads in flight per thread (the strips are short: latency-bound)
+constexpr int XU_R = 4;
+__device__ __forceinline__ void update_halo_range(const FieldTable& T, int nx, int ny, int pitch, int depth, int4 ext,
+                                                  int part, int gtid, int gsize) {
+  const int ring = 2 * depth * (nx + 1 + 2 * depth) + 2 * depth * (ny + 1);
+  const int total = ring * T.n;
+  for (int i0 = gtid; i0 < total; i0 += gsize * XU_R) {
+    double v[XU_R], sg[XU_R];
+    double* dst[XU_R];
+#pragma unroll
+    for (int u = 0; u < XU_R; ++u) {
+      const int i = i0 + u * gsize;
+      dst[u] = nullptr;
+      if (i < total) {
+        const double* src = update_halo_source(T.f[i / ring], nx, ny, pitch, depth, ext.x, ext.y, ext.z, ext.w, i % ring,
+                                               part, dst[u], sg[u]);
+        if (src) v[u] = *src;
+        else dst[u] = nullptr;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < XU_R; ++u)
+      if (dst[u]) *dst[u] = sg[u] * v[u];
+  }
 }
 __global__ void __launch_bounds__(256)
     update_halo_kernel(FieldTable T, int nx, int ny, int pitch, int depth, int ext_left, int ext_right,
@@ -559,19 +605,25 @@ __global__ void __launch_bounds__(256)
         for (int z = 0; z < A.nflag; ++z)
           asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.flag_out[z]), "l"(A.seq) : "memory");
       }
+    }
+  }
+  // The reflective boundary of the external faces (update_halo_kernel_c.c) in the same launch.  Almost all of it
+  // mirrors the chunk's own cells and is done now, while the neighbours' strips are on their way ...
+  const bool reflect = (ext.x | ext.y | ext.z | ext.w) != 0;
+  if (reflect) update_halo_range(T, nx, ny, pitch, depth, ext, A.nflag > 0 ? 1 : 0, gtid, gsize);
+  if (A.nflag > 0) {
+    if (threadIdx.x == 0) {
       for (int z = 0; z < A.nflag; ++z) spin_until_ge(A.flag_in[z], A.seq, timeout_ns, err, 1, rank, z);
       trace_max(trace, 3);
     }
     __syncthreads();
     exchange_copy<true>(T, nx, ny, pitch, depth, A, gtid, gsize);
-  }
-  // the reflective boundary of the external faces (update_halo_kernel_c.c) in the same launch: its corner cells
-  // mirror halo cells that the exchange has just delivered, hence the barrier
-  if (ext.x | ext.y | ext.z | ext.w) {
-    grid_barrier(counters + 3, barrier_target, timeout_ns, err, rank);
-    const int ring = 2 * depth * (nx + 1 + 2 * depth) + 2 * depth * (ny + 1);
-    for (int i = gtid; i < ring * T.n; i += gsize)
-      update_halo_item(T.f[i / ring], nx, ny, pitch, depth, ext.x, ext.y, ext.z, ext.w, i % ring);
+    // ... except the few cells beyond an external face that mirror halo cells the exchange has just delivered (the
+    // corner blocks between an external face and a face with a neighbour): after the unpack, hence the barrier
+    if (reflect) {
+      grid_barrier(counters + 3, barrier_target, timeout_ns, err, rank);
+      update_halo_range(T, nx, ny, pitch, depth, ext, 2, gtid, gsize);
+    }
   }
   trace_max(trace, 1);
 }
@@ -777,7 +829,7 @@ static void p2p_exchange(const Grid& g, const HaloArgs& h, const HaloArgs* bc) {
   if (ctas > max_ctas) ctas = max_ctas;
   unsigned int* counters = (unsigned int*)(PP.mine + 256);
   PP.arrive_total += (A.nflag > 0) ? (unsigned)ctas : 0u;
-  if (reflect) PP.barrier_total += (unsigned)ctas;
+  if (reflect && A.nflag > 0) PP.barrier_total += (unsigned)ctas;
   {
     LaunchScope ls("halo_exchange_p2p");
     launch_pdl(halo_exchange_kernel, dim3((unsigned)ctas), dim3(256), 0, stream(), T, g.nx, g.ny, g.pitch, h.depth, A, counters,
