@@ -197,7 +197,9 @@ def parity_check(deck_name, dts, summaries):
     G = json.load(open(path))
     n = min(len(dts), len(G["dt"]))
     bad = next((i for i in range(n) if dts[i] != G["dt"][i]), None)
-    gold = {int(r["step"]): r for r in G["summaries"]}
+    # the huge decks carry the reference run's sums re-evaluated in 80-bit pairwise arithmetic: the reference's own
+    # serial fp64 accumulation is only good to ~1e-9 at 15360^2 cells (tests/golden/make_golden.py: exact_summary)
+    gold = {int(r["step"]): r for r in (G.get("summaries_exact") or G["summaries"])}
     worst, rows = 0.0, 0
     for r in summaries:
         g = gold.get(int(r["step"]))

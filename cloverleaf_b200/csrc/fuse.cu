@@ -21,6 +21,8 @@
 // Every fused kernel executes the same per-cell arithmetic, in the same order, as the single-call kernels
 // (lagrange.cuh), so every array the host can observe afterwards is bit-identical (tests/test_gpu_run.py,
 // tests/test_gpu_fusion.py run both ways and compare all 15 fields including halos).
+#include <cstring>
+
 #include "clover_b200.h"
 #include "common.cuh"
 #include "lagrange.cuh"
@@ -821,6 +823,26 @@ static bool dead_after(const Op* q, size_t n, size_t from, const double* arr) {
 
 static int g_ctas_per_sm_timestep[2] = {0, 0};
 
+// the viscosity halo update of the timestep pattern, waiting to be merged into the next pressure halo update
+struct PendingHalo {
+  bool active = false, has_ex = false, has_uh = false;
+  Grid g{};
+  HaloArgs ex{}, uh{};
+};
+static PendingHalo g_pending_halo;
+static bool merge_halo_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("CLOVER_B200_MERGE_HALO") ? atoi(getenv("CLOVER_B200_MERGE_HALO")) : 1;
+  return v != 0;
+}
+bool pending_halo_exists() { return g_pending_halo.active; }
+void run_pending_halo() {
+  PendingHalo& P = g_pending_halo;
+  if (!P.active) return;
+  P.active = false;
+  run_exchange_then_halo(P.g, P.has_ex ? &P.ex : nullptr, P.has_uh ? &P.uh : nullptr);
+}
+
 // ---- T: ideal_gas -> halo{d0,e0,p,u0,v0} -> viscosity -> halo{q} -> calc_dt -------------------------------------
 static size_t fuse_timestep(const Op* q, size_t n, size_t i) {
   const Op& ig = q[i];
@@ -913,15 +935,19 @@ static size_t fuse_timestep(const Op* q, size_t n, size_t i) {
     note_fused_allreduce(0, 1, true, RT.all != nullptr);
   }
   if (ex2 || uh2) {
-    // Nothing reads the viscosity halo before accelerate: its exchange + reflective boundary go to the side stream
-    // and overlap the dt reduction, the host's dt read and the PdV predictor (which joins, fuse_predict below).
-    HaloArgs hx, hu;
-    if (ex2) hx = halo_args(*ex2, -1);
-    if (uh2) hu = halo_args(*uh2, -1);
-    const bool side = overlap_enabled();
-    if (side) side_begin();
-    run_exchange_then_halo(g, ex2 ? &hx : nullptr, uh2 ? &hu : nullptr);
-    if (side) side_end();
+    // Nothing reads the viscosity halo before accelerate (SURVEY 8a'): its exchange + reflective boundary are not
+    // issued here but kept pending, and ride along with the pressure exchange of the PdV predictor pattern, one
+    // NVLink round trip later in the step instead of two (fuse_predict below).  Anything else that comes first --
+    // another call sequence, a download, the end of the run -- issues them on their own (runtime.cu: flush_deferred).
+    PendingHalo& P = g_pending_halo;
+    if (P.active) run_pending_halo();
+    P.active = true;
+    P.g = g;
+    P.has_ex = ex2 != nullptr;
+    P.has_uh = uh2 != nullptr;
+    if (ex2) P.ex = halo_args(*ex2, -1);
+    if (uh2) P.uh = halo_args(*uh2, -1);
+    if (!(is_resident() && fusion_enabled() && merge_halo_enabled())) run_pending_halo();
   }
   return k - i;
 }
@@ -996,11 +1022,23 @@ static size_t fuse_predict(const Op* q, size_t n, size_t i) {
                                                                          qv, ss, x0, y0);
     }
   }
-  join_side();  // the viscosity exchange of the timestep pattern, if it is still in flight
+  join_side();
   {
     HaloArgs hx, hu;
     if (ex) hx = halo_args(*ex, -1);
     if (uh) hu = halo_args(*uh, -1);
+    // the pending viscosity halo update (fuse_timestep) rides along: same depth, same chunk, one more cell field
+    PendingHalo& P = g_pending_halo;
+    if (P.active && P.g.nx == g.nx && P.g.ny == g.ny && P.has_ex == (ex != nullptr) && P.has_uh == (uh != nullptr) &&
+        (!ex || P.ex.depth == hx.depth) && (!uh || (P.uh.depth == hu.depth && memcmp(P.uh.ext, hu.ext, sizeof(hu.ext)) == 0))) {
+      for (int f = 0; f < 15; ++f) {
+        if (ex && P.ex.fields[f]) { hx.fields[f] = 1; hx.host[f] = P.ex.host[f]; }
+        if (uh && P.uh.fields[f]) { hu.fields[f] = 1; hu.host[f] = P.uh.host[f]; }
+      }
+      P.active = false;
+    } else {
+      run_pending_halo();
+    }
     run_exchange_then_halo(g, ex ? &hx : nullptr, uh ? &hu : nullptr);
   }
   run_revert(g, density0, density1, energy0, energy1);  // a lazy copy in resident mode

@@ -70,6 +70,9 @@ static const struct { int x_inc, y_inc, m; double sx, sy; Kind kind; } kFieldGeo
 __device__ __forceinline__ const double* update_halo_source(const FieldDesc& F, int nx, int ny, int pitch, int depth,
                                                             int ext_left, int ext_right, int ext_bottom, int ext_top, int t,
                                                             int part, double*& dst, double& sign);
+__device__ __forceinline__ const double* update_halo_cell(const FieldDesc& F, int nx, int ny, int pitch, int ext_left,
+                                                          int ext_right, int ext_bottom, int ext_top, int jd, int kd,
+                                                          int part, double*& dst, double& sign);
 __device__ __forceinline__ void update_halo_item(const FieldDesc& F, int nx, int ny, int pitch, int depth, int ext_left,
                                                  int ext_right, int ext_bottom, int ext_top, int t, int part = 0) {
   double* dst;
@@ -95,6 +98,12 @@ __device__ __forceinline__ const double* update_halo_source(const FieldDesc& F, 
     kd = 1 + (u % H);
     jd = side == 0 ? 1 - r : nx + F.x_inc + r;
   }
+  return update_halo_cell(F, nx, ny, pitch, ext_left, ext_right, ext_bottom, ext_top, jd, kd, part, dst, sign);
+}
+// the same for one halo cell (jd, kd) given directly
+__device__ __forceinline__ const double* update_halo_cell(const FieldDesc& F, int nx, int ny, int pitch, int ext_left,
+                                                          int ext_right, int ext_bottom, int ext_top, int jd, int kd,
+                                                          int part, double*& dst, double& sign) {
   const bool out_x = jd < 1 || jd > nx + F.x_inc, out_y = kd < 1 || kd > ny + F.y_inc;
   const bool refl_x = (jd < 1 && ext_left) || (jd > nx + F.x_inc && ext_right);
   const bool refl_y = (kd < 1 && ext_bottom) || (kd > ny + F.y_inc && ext_top);
@@ -116,27 +125,40 @@ __device__ __forceinline__ const double* update_halo_source(const FieldDesc& F, 
   return F.p + idx2(pitch, js, ks);
 }
 // grid-stride reflection with XU_R independent loads in flight per thread (the strips are short: latency-bound)
-constexpr int XU_R = 4;
+// Reflection inside the exchange kernel: one WARP per segment of SEG cells of one halo line (a field's row r beyond
+// the bottom / top face, corners included, or its column r beyond the left / right face), SEG/32 independent loads in
+// flight per lane.  The segment is decoded once per warp; per cell only an add remains (the flat one-thread-per-ring-
+// index form above costs ~100 instructions of integer division per cell, which dominated the exchange kernel).
+constexpr int SEG = 256, SEG_U = SEG / 32;
 __device__ __forceinline__ void update_halo_range(const FieldTable& T, int nx, int ny, int pitch, int depth, int4 ext,
                                                   int part, int gtid, int gsize) {
-  const int ring = 2 * depth * (nx + 1 + 2 * depth) + 2 * depth * (ny + 1);
-  const int total = ring * T.n;
-  for (int i0 = gtid; i0 < total; i0 += gsize * XU_R) {
-    double v[XU_R], sg[XU_R];
-    double* dst[XU_R];
+  const int lane = gtid & 31, warp = gtid >> 5, nwarps = gsize >> 5;
+  const int maxlen = (nx > ny ? nx : ny) + 1 + 2 * depth;
+  const int nseg = (maxlen + SEG - 1) / SEG;
+  const int lines = T.n * 4 * depth;  // per field: 4 sides x depth lines
+  for (int sidx = warp; sidx < lines * nseg; sidx += nwarps) {
+    const int line = sidx / nseg, seg = sidx - line * nseg;
+    const int f = line / (4 * depth), q = line - f * 4 * depth, side = q / depth, r = q - side * depth + 1;
+    const FieldDesc& F = T.f[f];
+    // side 0 bottom, 1 top: jd runs over 1-depth .. nx+x_inc+depth; side 2 left, 3 right: kd runs over 1 .. ny+y_inc
+    const int len = side < 2 ? nx + F.x_inc + 2 * depth : ny + F.y_inc;
+    double v[SEG_U], sg[SEG_U];
+    double* dst[SEG_U];
 #pragma unroll
-    for (int u = 0; u < XU_R; ++u) {
-      const int i = i0 + u * gsize;
+    for (int u = 0; u < SEG_U; ++u) {
+      const int e = seg * SEG + u * 32 + lane;
       dst[u] = nullptr;
-      if (i < total) {
-        const double* src = update_halo_source(T.f[i / ring], nx, ny, pitch, depth, ext.x, ext.y, ext.z, ext.w, i % ring,
-                                               part, dst[u], sg[u]);
+      if (e < len) {
+        int jd, kd;
+        if (side < 2) { jd = 1 - depth + e; kd = side == 0 ? 1 - r : ny + F.y_inc + r; }
+        else          { kd = 1 + e;         jd = side == 2 ? 1 - r : nx + F.x_inc + r; }
+        const double* src = update_halo_cell(F, nx, ny, pitch, ext.x, ext.y, ext.z, ext.w, jd, kd, part, dst[u], sg[u]);
         if (src) v[u] = *src;
         else dst[u] = nullptr;
       }
     }
 #pragma unroll
-    for (int u = 0; u < XU_R; ++u)
+    for (int u = 0; u < SEG_U; ++u)
       if (dst[u]) *dst[u] = sg[u] * v[u];
   }
 }
@@ -473,28 +495,6 @@ struct XArgs {
   unsigned long long seq;
 };
 
-// strip element t of field F on `face` -> field cell (j,k) and message index; only the rank's own rows (left/right)
-// resp. columns (bottom/top) travel, the corners have their own messages
-__device__ __forceinline__ void message_index(const FieldDesc& F, int nx, int ny, int depth, int face, bool unpack,
-                                              int t, int& j, int& k, int& index, bool& valid) {
-  if (face < 2) {
-    const int span = ny + F.y_inc + 2 * depth;
-    const int jj = t % depth + 1, kk = t / depth;
-    k = kk - depth + 1;
-    valid = t < span * depth && k >= 1 && k <= ny + F.y_inc;
-    index = F.offset * depth * (ny + 5) + (jj - 1) + kk * depth;
-    if (face == 0) j = unpack ? 1 - jj : 1 + F.x_inc - 1 + jj;
-    else           j = unpack ? nx + F.x_inc + jj : nx + 1 - jj;
-  } else {
-    const int span = nx + F.x_inc + 2 * depth;
-    const int kk = t / span + 1, jx = t % span;
-    j = jx - depth + 1;
-    valid = t < span * depth && j >= 1 && j <= nx + F.x_inc;
-    index = F.offset * depth * (nx + 5) + (kk - 1) + jx * depth;
-    if (face == 2) k = unpack ? 1 - kk : 1 + F.y_inc - 1 + kk;
-    else           k = unpack ? ny + F.y_inc + kk : ny + 1 - kk;
-  }
-}
 // corner element t (= (kk-1)*depth + jj-1) of field F: the cell I send towards corner c / the halo cell I fill at c
 __device__ __forceinline__ void corner_index(const FieldDesc& F, int nx, int ny, int depth, int c, bool unpack, int t,
                                              int& j, int& k) {
@@ -509,39 +509,48 @@ __device__ __forceinline__ void corner_index(const FieldDesc& F, int nx, int ny,
   }
 }
 
-// A few CTAs move all strips: every thread keeps XU independent loads in flight (the copy is latency-bound: the
-// strips are a few hundred KB, the sources are strided rows of the fields or the peers' freshly written slots).
-constexpr int XU = 4;
+// A few CTAs move all strips: one WARP per segment of SEG cells of one strip line (field f, strip row / column r of a
+// face), SEG/32 independent loads in flight per lane; the segment is decoded once per warp (the copy is latency-bound:
+// a few hundred KB, strided columns of the fields or the peers' freshly written slots).  Message layout = the
+// reference's (pack_kernel_c.c): left/right index = off + (r-1) + (k+depth-1)*depth, bottom/top off + (r-1) +
+// (j+depth-1)*depth, off = field ordinal * depth * (edge+5); only own rows / columns travel (corners separately).
 template <bool UNPACK>
 __device__ __forceinline__ void exchange_copy(const FieldTable& T, int nx, int ny, int pitch, int depth, const XArgs& A,
                                               int gtid, int gsize) {
-  for (int z = 0; z < A.nface; ++z) {
+  const int lane = gtid & 31, warp = gtid >> 5, nwarps = gsize >> 5;
+  const int maxlen = (nx > ny ? nx : ny) + 1;
+  const int nseg = (maxlen + SEG - 1) / SEG;
+  const int lines = T.n * depth;  // per face
+  for (int sidx = warp; sidx < A.nface * lines * nseg; sidx += nwarps) {
+    const int z = sidx / (lines * nseg), w = sidx - z * lines * nseg, line = w / nseg, seg = w - line * nseg;
+    const int f = line / depth, r = line - f * depth + 1;
     const int face = A.face[z];
-    const int per_field = ((face < 2 ? ny : nx) + 1 + 2 * depth) * depth;
-    const int total = per_field * T.n;
-    for (int i0 = gtid; i0 < total; i0 += gsize * XU) {
-      double v[XU];
-      double* dst[XU];
+    const FieldDesc& F = T.f[f];
+    const int len = face < 2 ? ny + F.y_inc : nx + F.x_inc;  // own rows (left/right) resp. columns (bottom/top)
+    const int off = F.offset * depth * ((face < 2 ? ny : nx) + 5) + (r - 1);
+    int jfix = 0, kfix = 0;  // the fixed coordinate of this line
+    if (face == 0) jfix = UNPACK ? 1 - r : F.x_inc + r;
+    if (face == 1) jfix = UNPACK ? nx + F.x_inc + r : nx + 1 - r;
+    if (face == 2) kfix = UNPACK ? 1 - r : F.y_inc + r;
+    if (face == 3) kfix = UNPACK ? ny + F.y_inc + r : ny + 1 - r;
+    double* const slot = UNPACK ? A.fmine[z] : A.fbuf[z];
+    double v[SEG_U];
+    double* dst[SEG_U];
 #pragma unroll
-      for (int u = 0; u < XU; ++u) {
-        const int i = i0 + u * gsize;
-        dst[u] = nullptr;
-        if (i < total) {
-          const int f = i / per_field, t = i - f * per_field;
-          const FieldDesc& F = T.f[f];
-          int j, k, index;
-          bool valid;
-          message_index(F, nx, ny, depth, face, UNPACK, t, j, k, index, valid);
-          if (valid) {
-            if (UNPACK) { v[u] = __ldcg(A.fmine[z] + index); dst[u] = F.p + idx2(pitch, j, k); }
-            else        { v[u] = F.p[idx2(pitch, j, k)];     dst[u] = A.fbuf[z] + index; }
-          }
-        }
+    for (int u = 0; u < SEG_U; ++u) {
+      const int e = seg * SEG + u * 32 + lane;  // 0-based position along the face: cell 1+e
+      dst[u] = nullptr;
+      if (e < len) {
+        const int j = face < 2 ? jfix : 1 + e, k = face < 2 ? 1 + e : kfix;
+        double* cell = F.p + idx2(pitch, j, k);
+        double* msg = slot + off + (e + depth) * depth;  // ((1+e) + depth - 1) * depth
+        if (UNPACK) { v[u] = __ldcg(msg); dst[u] = cell; }
+        else        { v[u] = *cell;       dst[u] = msg; }
       }
-#pragma unroll
-      for (int u = 0; u < XU; ++u)
-        if (dst[u]) *dst[u] = v[u];
     }
+#pragma unroll
+    for (int u = 0; u < SEG_U; ++u)
+      if (dst[u]) *dst[u] = v[u];
   }
   const int per_corner = depth * depth;
   for (int i = gtid; i < A.ncorner * T.n * per_corner; i += gsize) {
@@ -598,12 +607,16 @@ __global__ void __launch_bounds__(256)
     exchange_copy<false>(T, nx, ny, pitch, depth, A, gtid, gsize);
     // publish: the last CTA to arrive tells every peer
     __syncthreads();
+    trace_max(trace, 4);  // [4] = strips written into the neighbours' slots
     if (threadIdx.x == 0) {
       __threadfence_system();
       if (atomicAdd(counters + 0, 1u) + 1 == arrive_target) {
+        // one system-scope fence (it is cumulative over the other CTAs' strips, ordered before it by their fence +
+        // ticket), then the flags go out back to back as relaxed stores -- a st.release per flag would serialise one
+        // NVLink round trip per neighbour
         __threadfence_system();
         for (int z = 0; z < A.nflag; ++z)
-          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.flag_out[z]), "l"(A.seq) : "memory");
+          asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(A.flag_out[z]), "l"(A.seq) : "memory");
       }
     }
   }
@@ -618,11 +631,25 @@ __global__ void __launch_bounds__(256)
     }
     __syncthreads();
     exchange_copy<true>(T, nx, ny, pitch, depth, A, gtid, gsize);
+    trace_max(trace, 5);  // [5] = unpacked
     // ... except the few cells beyond an external face that mirror halo cells the exchange has just delivered (the
     // corner blocks between an external face and a face with a neighbour): after the unpack, hence the barrier
     if (reflect) {
       grid_barrier(counters + 3, barrier_target, timeout_ns, err, rank);
-      update_halo_range(T, nx, ny, pitch, depth, ext, 2, gtid, gsize);
+      trace_max(trace, 6);  // [6] = past the grid barrier
+      // part 2 lives in the four depth x depth corner blocks only: enumerate those (a scan of the whole ring for them
+      // cost 15-20 us of index arithmetic)
+      const int per_corner = depth * depth;
+      for (int i = gtid; i < T.n * 4 * per_corner; i += gsize) {
+        const int f = i / (4 * per_corner), r = i - f * 4 * per_corner, c = r / per_corner, t = r - c * per_corner;
+        const FieldDesc& F = T.f[f];
+        const int jj = t % depth + 1, kk = t / depth + 1;
+        const int jd = (c & 1) ? nx + F.x_inc + jj : 1 - jj, kd = (c & 2) ? ny + F.y_inc + kk : 1 - kk;
+        double* dst;
+        double sign;
+        const double* src = update_halo_cell(F, nx, ny, pitch, ext.x, ext.y, ext.z, ext.w, jd, kd, 2, dst, sign);
+        if (src) *dst = sign * *src;
+      }
     }
   }
   trace_max(trace, 1);
@@ -824,7 +851,7 @@ static void p2p_exchange(const Grid& g, const HaloArgs& h, const HaloArgs* bc) {
     if (const char* e = getenv("CLOVER_B200_XCTAS")) max_ctas = atoi(e) > 0 ? atoi(e) : max_ctas;
     if (max_ctas > sm_count()) max_ctas = sm_count();
   }
-  int ctas = (int)((elements + 256 * XU - 1) / (256 * XU));
+  int ctas = (int)((elements + 256 * SEG_U - 1) / (256 * SEG_U));
   if (ctas < 1) ctas = 1;
   if (ctas > max_ctas) ctas = max_ctas;
   unsigned int* counters = (unsigned int*)(PP.mine + 256);

@@ -332,12 +332,18 @@ struct RingPairs {
   double* b[4];
   int ext[4];  // 0 cell data (update range 1..nx x 1..ny), 1 vertex data (1..nx+1 x 1..ny+1)
 };
-__global__ void __launch_bounds__(256) ring_swap_kernel(RingPairs P, int nx, int ny, int pitch) {
+__global__ void __launch_bounds__(256) ring_swap_kernel(RingPairs P, int nx, int ny, int pitch, unsigned long long* trace) {
+  trace_min(trace, 0);
+  pdl_wait();     // (programmatic dependent launch, common.cuh: the launch latency overlaps the previous kernel's tail)
+  pdl_trigger();
   const int e = P.ext[blockIdx.y];
   const int W = nx + 4 + e, H = ny + 4 + e;        // Fortran extent (-1..nx+2+e) x (-1..ny+2+e)
   const int n_bt = 4 * W, n_lr = 4 * (H - 4);      // two full rows below + above, two columns left + right
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_bt + n_lr) return;
+  if (t >= n_bt + n_lr) {
+    trace_max(trace, 1);
+    return;
+  }
   int j, k;
   if (t < n_bt) {
     const int r = t / W;
@@ -354,6 +360,7 @@ __global__ void __launch_bounds__(256) ring_swap_kernel(RingPairs P, int nx, int
   const double va = a[i], vb = b[i];
   a[i] = vb;
   b[i] = va;
+  trace_max(trace, 1);
 }
 
 // copy of one array's update range (materialisation of a lazy copy, runtime.cu)
@@ -490,7 +497,7 @@ void run_reset_field(const Grid& g, double* density0, double* density1, double* 
     {
       const int ring = 4 * (g.nx + 5) + 4 * (g.ny + 1);
       LaunchScope ls("reset_field_swap");
-      ring_swap_kernel<<<dim3((unsigned)((ring + 255) / 256), 4), 256, 0, stream()>>>(P, g.nx, g.ny, g.pitch);
+      launch_pdl(ring_swap_kernel, dim3((unsigned)((ring + 255) / 256), 4), dim3(256), 0, stream(), P, g.nx, g.ny, g.pitch, ls.trace);
     }
     for (int i = 0; i < 4; ++i) lazy_copy(g, h1[i], h0[i], kinds[i]);
     return;

@@ -251,7 +251,15 @@ void submit(Op&& op) {
 }
 
 void flush_deferred() {
-  if (R.draining || R.queue.empty()) return;
+  if (R.draining) return;
+  // a held-back viscosity halo update (fuse.cu) waits for the PdV predictor pattern only; anything else first
+  // (another call, or a host-visible point with nothing recorded) gets it issued now
+  if (pending_halo_exists() && (R.queue.empty() || R.queue[0].kind != OP_PDV_PREDICT)) {
+    R.draining = true;
+    run_pending_halo();
+    R.draining = false;
+  }
+  if (R.queue.empty()) return;
   R.draining = true;
   std::vector<Op> q;
   q.swap(R.queue);
@@ -261,6 +269,7 @@ void flush_deferred() {
     size_t used = R.fuse ? fuse_at(q.data(), q.size(), i) : 0;
     if (used == 0) {
       join_side();
+      if (pending_halo_exists()) run_pending_halo();  // (the predictor pattern did not match: nothing merges it)
       q[i].run();
       used = 1;
     }
@@ -454,7 +463,7 @@ void finish() {
 LaunchScope::LaunchScope(const char* n) : name(n), trace(nullptr) {
   if (R.profiling) CLV_CUDA(cudaEventRecord(R.ev0, R.stream));
   if (R.trace_on && R.trace_names.size() < TRACE_CAP) {
-    trace = R.d_trace + 4 * R.trace_names.size();
+    trace = R.d_trace + 8 * R.trace_names.size();
     R.trace_names.push_back(n);
   }
   R.cur_trace = trace;
@@ -902,7 +911,7 @@ void clover_b200_set_tma_(int* on) {
 void clover_b200_profile_reset_(void) { R.prof.clear(); }
 
 // In-situ timeline: with *on != 0 every launch from now on gets a slot of four %globaltimer stamps (common.cuh);
-// trace_dump_ writes "index,name,start_ns,end_ns,wait_begin_ns,wait_end_ns" (relative to the first start; empty
+// trace_dump_ writes "index,name,start_ns,end_ns,wait_begin_ns,wait_end_ns,packed_ns,unpacked_ns,barrier_ns" (relative to the first start; empty
 // fields where a kernel has no such stamp) and clears the record.  Unlike the event profile this does not serialise
 // the launches: it shows the step as it really runs (overlap of the halo exchange with interior tiles, gaps).
 void clover_b200_trace_(int* on) {
@@ -910,10 +919,14 @@ void clover_b200_trace_(int* on) {
   flush_deferred();
   join_side();
   CLV_CUDA(cudaStreamSynchronize(R.stream));
-  if (*on && !R.d_trace) CLV_CUDA(cudaMalloc(&R.d_trace, TRACE_CAP * 4 * sizeof(unsigned long long)));
+  if (*on && !R.d_trace) CLV_CUDA(cudaMalloc(&R.d_trace, TRACE_CAP * 8 * sizeof(unsigned long long)));
   if (*on) {
-    std::vector<unsigned long long> init(TRACE_CAP * 4);
-    for (size_t i = 0; i < TRACE_CAP; ++i) { init[4 * i] = ~0ull; init[4 * i + 1] = 0; init[4 * i + 2] = ~0ull; init[4 * i + 3] = 0; }
+    std::vector<unsigned long long> init(TRACE_CAP * 8);
+    for (size_t i = 0; i < TRACE_CAP; ++i) {
+      for (int k = 0; k < 8; ++k) init[8 * i + k] = 0;  // stamps folded with max
+      init[8 * i] = ~0ull;                               // [0], [2]: folded with min
+      init[8 * i + 2] = ~0ull;
+    }
     CLV_CUDA(cudaMemcpy(R.d_trace, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
     R.trace_names.clear();
   }
@@ -925,23 +938,25 @@ void clover_b200_trace_dump_(const char* path) {
   join_side();
   CLV_CUDA(cudaStreamSynchronize(R.stream));
   const size_t n = R.trace_names.size();
-  std::vector<unsigned long long> h(4 * (n ? n : 1));
-  if (n) CLV_CUDA(cudaMemcpy(h.data(), R.d_trace, 4 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  std::vector<unsigned long long> h(8 * (n ? n : 1));
+  if (n) CLV_CUDA(cudaMemcpy(h.data(), R.d_trace, 8 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   FILE* f = fopen(path, "w");
   if (!f) fatal("trace_dump: cannot write %s", path);
   unsigned long long t0 = ~0ull;
   for (size_t i = 0; i < n; ++i)
-    if (h[4 * i] < t0) t0 = h[4 * i];
-  fprintf(f, "index,name,start_ns,end_ns,wait_begin_ns,wait_end_ns\n");
+    if (h[8 * i] < t0) t0 = h[8 * i];
+  fprintf(f, "index,name,start_ns,end_ns,wait_begin_ns,wait_end_ns,packed_ns,unpacked_ns,barrier_ns\n");
   for (size_t i = 0; i < n; ++i) {
     fprintf(f, "%zu,%s,", i, R.trace_names[i]);
-    if (h[4 * i] != ~0ull) fprintf(f, "%llu", h[4 * i] - t0);
+    if (h[8 * i] != ~0ull) fprintf(f, "%llu", h[8 * i] - t0);
     fprintf(f, ",");
-    if (h[4 * i + 1] != 0) fprintf(f, "%llu", h[4 * i + 1] - t0);
+    if (h[8 * i + 1] != 0) fprintf(f, "%llu", h[8 * i + 1] - t0);
     fprintf(f, ",");
-    if (h[4 * i + 2] != ~0ull) fprintf(f, "%llu", h[4 * i + 2] - t0);
-    fprintf(f, ",");
-    if (h[4 * i + 3] != 0) fprintf(f, "%llu", h[4 * i + 3] - t0);
+    if (h[8 * i + 2] != ~0ull) fprintf(f, "%llu", h[8 * i + 2] - t0);
+    for (int k = 3; k < 7; ++k) {
+      fprintf(f, ",");
+      if (h[8 * i + k] != 0) fprintf(f, "%llu", h[8 * i + k] - t0);
+    }
     fprintf(f, "\n");
   }
   fclose(f);

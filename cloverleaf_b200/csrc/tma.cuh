@@ -236,8 +236,12 @@ struct TileQueue {
 // Host: the counter pair for the next launch (runtime.cu).
 Tickets next_tickets();
 
+// 128-byte alignment of the dynamic shared memory by POINTER arithmetic: a round trip through uintptr_t makes the
+// compiler forget that the address is in the shared window, and every tile access then becomes a generic LD.E / ST.E
+// with a 64-bit address pair instead of LDS / STS with a 32-bit address and an immediate offset (SASS of the round-1
+// kernels: 50 LD.E.64 per tile loop, hundreds of IMAD / LEA of address arithmetic in issue-bound kernels).
 __device__ __forceinline__ unsigned char* align128(unsigned char* p) {
-  return reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 127) & ~(uintptr_t)127);
+  return p + ((128u - (smem_u32(p) & 127u)) & 127u);
 }
 #endif
 
