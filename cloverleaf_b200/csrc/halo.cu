@@ -1106,10 +1106,17 @@ static bool answer_from_fused(double* values, int n, bool is_min) {
 
 static void allreduce_host(double* values, int n, ncclRedOp_t op) {
   ensure_init();
-  flush_deferred();
-  if (!N.comm || N.nranks == 1) return;
+  if (!N.comm || N.nranks == 1) {
+    flush_deferred();
+    return;
+  }
   if (n > 16) fatal("allreduce of %d values (max 16)", n);
-  if (answer_from_fused(values, n, op == ncclMin)) return;
+  // Answered from what the reduction kernel left behind when nothing has been recorded since (the call the driver
+  // makes right after calc_dt / field_summary): no launch, and no flush either -- a flush here would issue the
+  // held-back viscosity halo update on its own instead of merged with the pressure exchange (fuse.cu).
+  if (deferred_queue_empty() && answer_from_fused(values, n, op == ncclMin)) return;
+  FA.valid = false;
+  flush_deferred();
   if (n <= 8 && chunk_registered()) {
     int one = 1, nx = chunk_nx(), ny = chunk_ny();
     if (p2p_setup(grid_of_noflush(&one, &nx, &one, &ny))) {

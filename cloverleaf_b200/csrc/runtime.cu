@@ -250,6 +250,8 @@ void submit(Op&& op) {
   if (R.queue.size() >= 1024) flush_deferred();
 }
 
+bool deferred_queue_empty() { return R.queue.empty(); }
+
 void flush_deferred() {
   if (R.draining) return;
   // a held-back viscosity halo update (fuse.cu) waits for the PdV predictor pattern only; anything else first
@@ -526,7 +528,7 @@ void wait_scalars(int base, double seq) {
   struct timeval t0;
   gettimeofday(&t0, nullptr);
   while (*flag != seq) {
-    if ((++spins & 0xfff) == 0) {
+    if ((++spins & 0xfffff) == 0) {  // ~every millisecond: a stream query takes microseconds and must not sit on the dt path
       const cudaError_t q = cudaStreamQuery(R.stream);
       if (q != cudaSuccess && q != cudaErrorNotReady) CLV_CUDA(q);
       if (q == cudaSuccess && *flag != seq) {  // the stream has drained and the kernel never wrote: cannot happen
