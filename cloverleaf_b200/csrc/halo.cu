@@ -164,10 +164,13 @@ __device__ __forceinline__ void update_halo_range(const FieldTable& T, int nx, i
 }
 __global__ void __launch_bounds__(256)
     update_halo_kernel(FieldTable T, int nx, int ny, int pitch, int depth, int ext_left, int ext_right,
-                       int ext_bottom, int ext_top, unsigned long long* trace) {
+                       int ext_bottom, int ext_top, unsigned long long* trace, int trigger_first) {
   trace_min(trace, 0);
+  // trigger_first: the predecessor is reset_field's ring swap, which touches halo rings only and has itself waited for
+  // the last compute kernel -- the next compute kernel's interior tiles may start next to it
+  if (trigger_first) pdl_trigger();
   pdl_wait();     // the kernel that produced the interior cells has completed
-  pdl_trigger();  // the next compute kernel may start its interior tiles (common.cuh: PDL)
+  if (!trigger_first) pdl_trigger();  // the next compute kernel may start its interior tiles (common.cuh: PDL)
   trace_min(trace, 2);
   update_halo_item(T.f[blockIdx.y], nx, ny, pitch, depth, ext_left, ext_right, ext_bottom, ext_top,
                    (int)(blockIdx.x * blockDim.x + threadIdx.x));
@@ -597,10 +600,11 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 __global__ void __launch_bounds__(256)
     halo_exchange_kernel(FieldTable T, int nx, int ny, int pitch, int depth, XArgs A, unsigned int* counters,
                          unsigned int arrive_target, unsigned int barrier_target, int4 ext, unsigned long long timeout_ns,
-                         double* err, int rank, unsigned long long* trace) {
+                         double* err, int rank, unsigned long long* trace, int trigger_first) {
   trace_min(trace, 0);
+  if (trigger_first) pdl_trigger();  // (behind reset_field's ring swap: see update_halo_kernel)
   pdl_wait();     // the kernel that produced the strips has completed
-  pdl_trigger();  // the next compute kernel may start: its interior tiles need none of what follows (common.cuh: PDL)
+  if (!trigger_first) pdl_trigger();  // the next compute kernel may start: its interior tiles need none of what follows
   trace_min(trace, 2);  // [2] = work begins (dependency satisfied); [3] = all neighbours' strips have arrived
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
   if (A.nflag > 0) {
@@ -857,10 +861,12 @@ static void p2p_exchange(const Grid& g, const HaloArgs& h, const HaloArgs* bc) {
   unsigned int* counters = (unsigned int*)(PP.mine + 256);
   PP.arrive_total += (A.nflag > 0) ? (unsigned)ctas : 0u;
   if (reflect && A.nflag > 0) PP.barrier_total += (unsigned)ctas;
+  const int trigger_first = ring_swap_just_launched() ? 1 : 0;
   {
     LaunchScope ls("halo_exchange_p2p");
     launch_pdl(halo_exchange_kernel, dim3((unsigned)ctas), dim3(256), 0, stream(), T, g.nx, g.ny, g.pitch, h.depth, A, counters,
-               PP.arrive_total, PP.barrier_total, ext, spin_timeout_ns(), device_error_record(), N.rank, ls.trace);
+               PP.arrive_total, PP.barrier_total, ext, spin_timeout_ns(), device_error_record(), N.rank, ls.trace,
+               trigger_first);
   }
   note_halo_launch();
 }
@@ -904,10 +910,11 @@ void run_update_halo(const Grid& g, const HaloArgs& h) {
     }
     const int ring = 2 * h.depth * (g.nx + 1 + 2 * h.depth) + 2 * h.depth * (g.ny + 1);
     const dim3 grid((unsigned)((ring + 255) / 256), (unsigned)T.n);
+    const int trigger_first = ring_swap_just_launched() ? 1 : 0;
     {
       LaunchScope ls("update_halo");
       launch_pdl(update_halo_kernel, grid, dim3(256), 0, stream(), T, g.nx, g.ny, g.pitch, h.depth, h.ext[0], h.ext[1],
-                 h.ext[2], h.ext[3], ls.trace);
+                 h.ext[2], h.ext[3], ls.trace, trigger_first);
     }
     note_halo_launch();
   }

@@ -499,6 +499,7 @@ void run_reset_field(const Grid& g, double* density0, double* density1, double* 
       LaunchScope ls("reset_field_swap");
       launch_pdl(ring_swap_kernel, dim3((unsigned)((ring + 255) / 256), 4), dim3(256), 0, stream(), P, g.nx, g.ny, g.pitch, ls.trace);
     }
+    note_ring_swap_launch();
     for (int i = 0; i < 4; ++i) lazy_copy(g, h1[i], h0[i], kinds[i]);
     return;
   }

@@ -78,6 +78,7 @@ struct Runtime {
   bool pdl = true;        // programmatic dependent launch ($CLOVER_B200_PDL=0 disables)
   bool split = true;      // interior tiles before the halo wait ($CLOVER_B200_SPLIT=0: wait before the first tile)
   bool halo_noted = false;  // the last launch was an exchange / update_halo kernel
+  bool ring_swap_noted = false;  // the last launch was reset_field's ring swap
   unsigned int* d_tickets = nullptr;  // ring of {tickets, exits} pairs (next_tickets)
   unsigned int ticket_turn = 0;
   bool trace_on = false;                 // in-situ timeline (clover_b200_trace_)
@@ -476,6 +477,7 @@ LaunchScope::~LaunchScope() {
   R.launches++;
   R.cur_trace = nullptr;
   R.halo_noted = false;  // halo.cu re-notes after its scope closes; any other launch ends the "just launched" state
+  R.ring_swap_noted = false;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) fatal("launch of %s failed: %s", name, cudaGetErrorString(e));
   if (R.profiling) {
@@ -700,6 +702,10 @@ Tickets next_tickets() {
 bool pdl_enabled() { return R.pdl && !R.profiling; }
 void note_halo_launch() { R.halo_noted = true; }
 bool halo_just_launched() { return R.halo_noted; }
+// reset_field's ring swap touches halo rings only and triggers its dependents after its own wait: the halo kernel that
+// follows it may trigger BEFORE its wait (its dependents' interior tiles then run next to the ring swap as well)
+void note_ring_swap_launch() { R.ring_swap_noted = true; }
+bool ring_swap_just_launched() { return R.ring_swap_noted && pdl_enabled(); }
 int dep_start_for(const TileOrder& o) { return (halo_just_launched() && pdl_enabled() && R.split) ? o.n_interior : 0; }
 
 // used by halo.cu
