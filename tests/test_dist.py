@@ -151,6 +151,26 @@ def test_nccl_ranks_match_single_gpu(tmp_path, world):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("world,nx,ny", [(2, 250, 130), (4, 250, 130), (4, 61, 37)])
+def test_ragged_chunks_match_single_gpu(tmp_path, world, nx, ny):
+    """Odd mesh sizes: 2 x 125x130, 4 x 125x65 and 4 chunks of 31/30 x 19/18 cells (clover_decompose gives the
+    remainder to the low-index chunks, clover.f90:150-170; unequal neighbours, tiles that are mostly rim, strips
+    shorter than a copy segment) through the peer-memory exchange: dt bit-identical to the oracle's single-chunk run."""
+    if _gpu_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import cloverleaf_b200
+    steps = 25
+    ranks = _run_world(tmp_path, world, "nccl", cloverleaf_b200.LIB_B200, nx, ny, steps)
+    dt1, s1 = _single(ORACLE_PORT, nx, ny, steps)
+    for r in ranks:
+        assert r["dt"] == dt1, "rank %d: dt differs from the oracle's single-chunk run" % r["rank"]
+    for a, b in zip(ranks[0]["summaries"], s1):
+        for k in ("volume", "mass", "ie", "ke", "pressure"):
+            assert abs(a[k] - b[k]) <= 1e-10 * max(abs(b[k]), 1e-300)
+    assert sum(r["chunk"]["x_max"] * r["chunk"]["y_max"] for r in ranks) == nx * ny
+
+
+@pytest.mark.gpu
 def test_nccl_transport_matches_single_gpu(tmp_path):
     """The fallback transport (ncclSend/ncclRecv + ncclAllReduce, CLOVER_B200_P2P=0) against the same oracle run."""
     if _gpu_count() < 2:
