@@ -519,6 +519,14 @@ def _main():
                               "frac": round(step_gbs / peak, 4), "frac_of_8TBs_nominal": round(step_gbs / 8000.0, 4),
                               "peak_source": peak_src},
             "kernels": kernels, "active_regime": active, "cpu_baseline": cpu, "parity": parity,
+            # what bounds the step at this N (in-situ timelines: profiles/r02_final_trace_8gpu_summary.txt)
+            "limiter": ("HBM streaming kernels at 0.66-0.92 of measured copy bandwidth (fp64 dependency chains + tile "
+                        "barriers: ncu stall reasons wait / barrier); dt hand-over to the host ~20 us/step" if world == 1 else
+                        "latency, not bandwidth: per step 5 halo exchanges of 17-27 us each (NVLink round trip + neighbour "
+                        "skew; hidden behind the next kernel's interior tiles only while that interior outlasts them), the dt "
+                        "hand-over (cross-rank fold waits for the slowest rank + host round trip, 30-45 us, nothing to "
+                        "overlap: the ABI returns dt by value) and ~3 us of prologue per launch; halo bytes are <0.3 % of "
+                        "NVLink bandwidth"),
         }
     # leave the device idle before the ranks part: nothing of ours may still be writing into a peer's memory
     lib.clover_b200_device_synchronize_()
