@@ -233,11 +233,17 @@ void clover_b200_comm_init_(int *nranks, int *rank, char *id128);
  * bottom/top; the values that land in the corner cells are identical (tests/test_dist.py, bench.py `parity`).
  * Fallback transport: device pack -> ncclSend/ncclRecv (left/right phase, then bottom/top) -> device unpack. */
 void clover_b200_exchange_(int *fields, int *depth);
-/* clover_min (clover.f90:3640-3656): minimum of one double over all ranks, result on every rank (peer-memory
- * mailboxes folded in rank order; fallback ncclAllReduce(min)). */
+/* clover_min (clover.f90:3640-3656): minimum of one double over all ranks, result on every rank.  Called right
+ * after calc_dt_kernel_c_ (timestep.f90:86-90) it costs no launch: the calc_dt launch has already folded the
+ * minimum over all ranks (peer-memory mailboxes, rank order) and this call returns min(*value, that minimum) --
+ * which is the all-rank minimum of *value provided *value = MIN(dt_min_val, bounds that are the same on every
+ * rank), as in timestep.f90; a *value above the dt_min_val calc_dt returned aborts with a message.  In any other
+ * position it is a stand-alone all-reduce over the same mailboxes (fallback transport: ncclAllReduce(min)). */
 void clover_b200_min_(double *value);
 /* clover_sum (clover.f90:3621-3637), n values at once, result on every rank (the reference reduces to rank 0
- * only); folded in rank order, so every rank holds bit-identical sums (fallback ncclAllReduce(sum)). */
+ * only); folded in rank order, so every rank holds bit-identical sums (fallback ncclAllReduce(sum)).  Called with
+ * the five sums field_summary_kernel_c_ has just returned (in the kernel's argument order: vol, mass, ie, ke,
+ * press) it costs no launch either: the field_summary launch folded them over all ranks already. */
 void clover_b200_sum_(double *values, int *n);
 
 /* Accounting for bench.py: kernels launched so far by this library, and (when enabled with
