@@ -12,6 +12,7 @@
 
 #include "clover_b200.h"
 #include "common.cuh"
+#include "tile_order.h"
 #include "tma.cuh"
 
 namespace clv {
@@ -619,55 +620,17 @@ const CUtensorMap* tensor_map_for(const Grid& g, const double* dev_ptr, int box_
 }
 
 namespace {
-std::map<std::tuple<int, int, int>, int2*> g_tile_orders;
-}
-const int2* tile_order(int ntx, int nty, int tw) {
-  constexpr int BAND_COLS = 4096;
-  const int band_tiles = (ntx * tw <= BAND_COLS + 256) ? ntx : (BAND_COLS / tw > 0 ? BAND_COLS / tw : 1);
-  const auto key = std::make_tuple(ntx, nty, band_tiles);
-  auto it = g_tile_orders.find(key);
-  if (it != g_tile_orders.end()) return it->second;
-  std::vector<int2> h;
-  h.reserve((size_t)ntx * nty);
-  for (int x0 = 0; x0 < ntx; x0 += band_tiles) {
-    const int w = (ntx - x0 < band_tiles) ? ntx - x0 : band_tiles;
-    for (int ty = 0; ty < nty; ++ty)
-      for (int tx = x0; tx < x0 + w; ++tx) h.push_back(make_int2(tx, ty));
-  }
-  if ((int)h.size() != ntx * nty) fatal("tile_order: %zu entries for %d x %d tiles", h.size(), ntx, nty);
-  int2* d = nullptr;
-  CLV_CUDA(cudaMalloc(&d, h.size() * sizeof(int2)));
-  CLV_CUDA(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice, R.stream));
-  CLV_CUDA(cudaStreamSynchronize(R.stream));
-  g_tile_orders[key] = d;
-  return d;
-}
-
-namespace {
 std::map<std::tuple<int, int, int, int, int, int, int, int, int, int>, TileOrder> g_split_orders;
 }
 TileOrder tile_order_split(int ntx, int nty, int tw, int th, int lo_x, int hi_x, int lo_y, int hi_y, int nx, int ny) {
-  constexpr int BAND_COLS = 4096;
-  const int band_tiles = (ntx * tw <= BAND_COLS + 256) ? ntx : (BAND_COLS / tw > 0 ? BAND_COLS / tw : 1);
   const auto key = std::make_tuple(ntx, nty, tw, th, lo_x, hi_x, lo_y, hi_y, nx, ny);
   auto it = g_split_orders.find(key);
   if (it != g_split_orders.end()) return it->second;
-  auto interior = [&](int tx, int ty) {
-    const int j0 = 1 + tx * tw, k0 = 1 + ty * th;
-    return j0 - lo_x >= 1 && j0 + tw - 1 + hi_x <= nx && k0 - lo_y >= 1 && k0 + th - 1 + hi_y <= ny;
-  };
-  std::vector<int2> h;
-  h.reserve((size_t)ntx * nty);
-  for (int pass = 0; pass < 2; ++pass) {  // 0: interior tiles, 1: rim tiles; each banded, row by row inside a band
-    for (int x0 = 0; x0 < ntx; x0 += band_tiles) {
-      const int w = (ntx - x0 < band_tiles) ? ntx - x0 : band_tiles;
-      for (int ty = 0; ty < nty; ++ty)
-        for (int tx = x0; tx < x0 + w; ++tx)
-          if (interior(tx, ty) == (pass == 0)) h.push_back(make_int2(tx, ty));
-    }
-    if (pass == 0) g_split_orders[key].n_interior = (int)h.size();
-  }
+  std::vector<TileXY> h;
+  const int n_interior = build_tile_order(ntx, nty, tw, th, lo_x, hi_x, lo_y, hi_y, nx, ny, h);  // tile_order.h
+  g_split_orders[key].n_interior = n_interior;
   if ((int)h.size() != ntx * nty) fatal("tile_order_split: %zu entries for %d x %d tiles", h.size(), ntx, nty);
+  static_assert(sizeof(TileXY) == sizeof(int2), "TileXY is uploaded as int2");
   int2* d = nullptr;
   CLV_CUDA(cudaMalloc(&d, h.size() * sizeof(int2)));
   CLV_CUDA(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(int2), cudaMemcpyHostToDevice, R.stream));

@@ -25,15 +25,14 @@ namespace clv {
 // Host: tensor map of `dev_ptr` (a field in the pitched layout of grid g) with a box_w x box_h box; cached.
 const CUtensorMap* tensor_map_for(const Grid& g, const double* dev_ptr, int box_w, int box_h);
 
-// Host: device table of the ntx*nty tile coordinates of a grid of tw-wide tiles, in the order the persistent CTAs walk
-// them (CTA b takes entries b, b+G, b+2G, ...; the kernels fetch an entry one iteration before they need it); cached
-// per shape.  Chunks up to ~4096 cells wide are walked row by row: the CTAs that run at the same time then stream long
-// contiguous row segments and the halo rows shared with the next tile row are still in L2 one tile row later.  Wider
-// chunks are walked down bands of ~4096 columns, which keeps both properties (a 15360-wide chunk walked row by row
-// re-fetched its halo rows from DRAM: ncu showed 1.16x - 2.1x the compulsory reads, against 1.00x - 1.05x at 3840).
-const int2* tile_order(int ntx, int nty, int tw);
-// The same table with the tiles whose input boxes lie entirely inside the cells 1..nx x 1..ny (no halo cell, hence
-// no dependence on a preceding halo exchange / reflective boundary) in front, banded as above, followed by the rim
+// Host: device table of the ntx*nty tile coordinates in the order the persistent CTAs' ticket queue hands them out;
+// cached per shape (runtime.cu; the order itself is plain C++ in tile_order.h).  Chunks up to ~4096 cells wide are
+// listed row by row: the CTAs that run at the same time then stream long contiguous row segments and the halo rows
+// shared with the next tile row are still in L2 one tile row later.  Wider chunks are walked down bands of ~4096
+// columns, which keeps both properties (a 15360-wide chunk walked row by row re-fetched its halo rows from DRAM: ncu
+// showed 1.16x - 2.1x the compulsory reads, against 1.00x - 1.05x at 3840).  Within that, the tiles whose input boxes
+// lie entirely inside the cells 1..nx x 1..ny (no halo cell, hence
+// no dependence on a preceding halo exchange / reflective boundary) come first, followed by the rim
 // tiles; n_interior = how many there are.  Tile (tx,ty) reads the columns 1+tx*tw-lo_x .. 1+(tx+1)*tw-1+hi_x and the
 // rows 1+ty*th-lo_y .. 1+(ty+1)*th-1+hi_y.  See "programmatic dependent launch" in common.cuh.
 struct TileOrder {
