@@ -533,6 +533,9 @@ __global__ void __launch_bounds__(CT_W* CT_BY)
 // the vertices / faces of the tile plus the extra row and column.  The arithmetic is that of
 // lagrange_correct_kernel, statement for statement.
 constexpr int LT_H = 8, LT_BH = LT_H + 2, LT_NARR = 9;
+#ifndef LC_FASTDIV
+#define LC_FASTDIV 1
+#endif
 constexpr int LT_OX = 2;  // box corner at j0-2: TMA needs a 16-byte aligned start, i.e. an even dim-0 coordinate (tma.cuh)
 enum { LA_XAREA = 0, LA_YAREA, LA_VOLUME, LA_DENSITY0, LA_ENERGY0, LA_PRESSURE, LA_VISCOSITY, LA_XVEL0, LA_YVEL0 };
 struct CorrectMaps {
@@ -635,7 +638,7 @@ __global__ void __launch_bounds__(W* LT_H / RPT, CPS)
         const double q11 = sq[c11], q01 = sq[c01], q10 = sq[c10], q00 = sq[c00];
         const double xv0 = su0[c11], yv0 = sv0[c11];
         const double nodal_mass = (d00 * w00 + d10 * w10 + d11 * w11 + d01 * w01) * 0.25;
-        const double s = 0.5 * dt / nodal_mass;
+        const double s = 0.5 * dt / nodal_mass;  // (the branch-free sequence was measured slower here: 0.322 vs 0.319 ms)
         double x = xv0 - s * (xa1 * (p11 - p01) + xa0 * (p10 - p00));
         double y = yv0 - s * (ya1 * (p11 - p10) + ya0 * (p01 - p00));
         xv[i] = x - s * (xa1 * (q11 - q01) + xa0 * (q10 - q00));
@@ -681,9 +684,24 @@ __global__ void __launch_bounds__(W* LT_H / RPT, CPS)
         const double bottom = ya0 * (y00 + y10 + b00 + b10) * 0.25 * dt;
         const double top = ya1 * (y01 + y11 + b01 + b11) * 0.25 * dt;
         const double total = right - left + top - bottom;
+#if LC_FASTDIV
+        // the three independent quotients of a cell through the branch-free IEEE sequence (common.cuh: Math<false>):
+        // with the operators each division ends a basic block and the three run strictly one after the other
+        bool bad = false;
+        double vc = Math<false>::div(vol, vol + total, bad);
+        double recip = Math<false>::rcp(vol, bad);
+        double pr = Math<false>::div(pres, rho0, bad);
+        if (bad && j0 + lx <= nx && k0 + ly <= ny) {  // (slots beyond the chunk hold zeros: never stored, never re-run)
+          vc = vol / (vol + total);
+          recip = 1.0 / vol;
+          pr = pres / rho0;
+        }
+        const double de = (pr + ddiv(visc, rho0)) * total * recip;
+#else
         const double vc = vol / (vol + total);
         const double recip = 1.0 / vol;
         const double de = (pres / rho0 + ddiv(visc, rho0)) * total * recip;
+#endif
         e1[r] = en0 - de;
         d1[r] = rho0 * vc;
       }
