@@ -346,6 +346,11 @@ def _main():
     done, ms, wall = timed_steps(d, args.steps)
     l1 = launches()
     hb1, hx1 = halo_counters()
+    p2p = ci(0)
+    lib.clover_b200_transport_(ctypes.byref(p2p))
+    transport = ("none (one rank)" if world == 1 else
+                 "peer memory over NVLink/NVSwitch (cudaIpc-mapped exchange blocks, own kernels); NCCL for bootstrap only"
+                 if p2p.value else "NCCL fallback (ncclSend/ncclRecv/ncclAllReduce)")
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(ms)
     cells = nx * ny
@@ -505,7 +510,7 @@ def _main():
             "metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": done,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic (deck-defined initial state, no RNG)",
-            "config": {"workload": workload, "chunks": chunks,
+            "config": {"workload": workload, "chunks": chunks, "transport": transport,
                        "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (25 * 8 * chunk_cells / 1e9),
                        "timing": "CUDA events on the library stream, max over ranks; host wall %.3f s" % wall},
             "clocks": clocks, "e2e": e2e, "gpu_launches": l1 - l0,

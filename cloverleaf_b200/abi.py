@@ -89,7 +89,7 @@ EXTENSION_SYMBOLS = [
     "clover_b200_profile_reset_", "clover_b200_copy_bytes_", "clover_b200_halo_bytes_", "clover_b200_event_record_",
     "clover_b200_event_elapsed_ms_", "clover_b200_pin_", "clover_b200_unpin_", "clover_b200_selftest_math_",
     "clover_b200_set_fusion_",
-    "clover_b200_set_tma_", "clover_b200_trace_", "clover_b200_trace_dump_",
+    "clover_b200_set_tma_", "clover_b200_trace_", "clover_b200_trace_dump_", "clover_b200_transport_",
 ]
 
 CELL_DATA, VERTEX_DATA, X_FACE_DATA, Y_FACE_DATA = 1, 2, 3, 4  # data.f90:68-71

@@ -1145,6 +1145,8 @@ static void allreduce_host(double* values, int n, ncclRedOp_t op) {
   CLV_CUDA(cudaMemcpyAsync(values, N.d_scal, n * sizeof(double), cudaMemcpyDeviceToHost, stream()));
   CLV_CUDA(cudaStreamSynchronize(stream()));
 }
+// *p2p = 1: halos and reductions travel through peer memory; 0: ncclSend/ncclRecv/ncclAllReduce (or one rank only)
+void clover_b200_transport_(int* p2p) { *p2p = (PP.on && N.nranks > 1) ? 1 : 0; }
 void clover_b200_halo_bytes_(long long* bytes, long long* exchanges) {
   flush_deferred();
   *bytes = PP.bytes_sent + PP.nccl_bytes;

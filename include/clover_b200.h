@@ -263,6 +263,8 @@ void clover_b200_copy_bytes_(long long *h2d, long long *d2h);
 /* Bytes this rank has written into its neighbours' memory (halo strips + corner blocks) and the number of
  * exchanges so far; bench.py reports the halo traffic against NVLink bandwidth from these. */
 void clover_b200_halo_bytes_(long long *bytes, long long *exchanges);
+/* Which transport the multi-rank data path uses: *p2p = 1 peer memory (default), 0 the NCCL fallback / one rank. */
+void clover_b200_transport_(int *p2p);
 
 /* Self-test of the library's branch-free fp64 div / rcp / sqrt against the compiler's IEEE operators
  * on *n pseudo-random + adversarial operand pairs: *mismatches must come back 0; *flagged counts
