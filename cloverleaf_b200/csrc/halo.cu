@@ -1,6 +1,8 @@
-// halo.cu -- reflective boundary (update_halo), halo message pack/unpack, the NCCL halo exchange and
-// scalar reductions that replace clover_exchange / clover_min / clover_sum, and the two set-up
-// kernels (initialise_chunk, generate_chunk).  fp64 CUDA for sm_100a.
+// halo.cu -- reflective boundary (update_halo), halo message pack/unpack (the ABI's clover_(un)pack_message_*_c_), the
+// halo exchange and scalar reductions that replace clover_exchange / clover_min / clover_sum -- our own kernels over
+// peer memory (NVLink / NVSwitch, cudaIpc-mapped exchange blocks), with ncclSend/ncclRecv/ncclAllReduce as the fallback
+// transport and NCCL as the bootstrap -- and the two set-up kernels (initialise_chunk, generate_chunk).  fp64 CUDA for
+// sm_100a.
 #include <dlfcn.h>
 #include <nccl.h>
 
