@@ -9,7 +9,9 @@
 //      one kernel: pressure of the four neighbours is recomputed from their density/energy (2 multiplies,
 //      bit-identical to the exchanged/reflected halo pressure because p is a pointwise function and the
 //      reflection of cell data is a plain copy), soundspeed and viscosity go straight into the dt minimum.
-//      17 algorithmic passes -> 10 (reads d0,e0,u0,v0,volume,xarea,yarea; writes p,q,soundspeed).
+//      17 algorithmic passes -> 9 (reads d0,e0,u0,v0,volume,xarea,yarea; writes p,q; the sound speed is consumed on
+//      chip and left unevaluated in memory -- runtime.cu: lazy_soundspeed -- unless the register variant runs).
+//      The viscosity halo update is held back and merged into the pressure halo update of pattern P.
 //   P  PdV predictor -> ideal_gas(d1,e1) -> [exchange][update_halo]{p} -> revert
 //      one kernel: the predicted density/energy live in registers only (revert would overwrite them);
 //      19 passes -> 10 or 11 (soundspeed is stored only if something reads it before it is next overwritten).
