@@ -491,6 +491,169 @@ static void launch_cell(const Grid& g, const CellMaps& M, const double* d_old, d
              dep_start_for(ord), current_trace());
 }
 
+
+// ====================================================================================================================
+// advec_cell, y sweep, "column march": the same arithmetic with NO intermediate planes and NO barriers between phases.
+// Thread (lx, grp) owns column j0+lx and the YM_R cells k0+grp*YM_R .. +YM_R-1 of a 32 x (8*YM_R) tile.  Everything a
+// face or a cell needs along y comes from the thread's own column of the staged boxes (pre_vol needs vol_flux_x at j and
+// j+1, which are inputs, not results), so the YM_R+1 face fluxes and YM_R cell updates of a thread are independent
+// straight-line work; the face on top of a group is evaluated twice (by the group above as its own) instead of passed
+// through shared memory behind a barrier.  Boxes: columns j0-2 .. j0+33, rows k0-2 .. k0+H+2.  The tiling covers the
+// rows 1 .. ny+2: the reference stores mass_flux_y up to face y_max+2 (advec_cell_kernel_c.c:219), cells beyond ny are
+// not updated.  ncu on the three-phase kernel: top stalls `wait` and `barrier`, 23 % of the rows of a box are halo.
+constexpr int YM_R = 4, YM_G = 8, YM_W = 32, YM_H = YM_G * YM_R, YM_BW = YM_W + 4, YM_BH = YM_H + 5, YM_STAGES = 2;
+using MarchRing = TileRing<CA_NARR, YM_BW, YM_BH, YM_STAGES>;
+constexpr int YM_SMEM = MarchRing::BYTES + 128;
+
+template <int SWEEP>
+__global__ void __launch_bounds__(YM_W* YM_G, 2)
+    advec_cell_ymarch_tma_kernel(const __grid_constant__ CellMaps M, const double* __restrict__ d_old, double* __restrict__ d_new,
+                                 const double* __restrict__ e_old, double* __restrict__ e_new,
+                                 double* __restrict__ mass_flux, const double* __restrict__ vertexd, int nx, int ny, int pitch,
+                                 int ntiles, const int2* __restrict__ order, Tickets tickets, int dep_start,
+                                 unsigned long long* trace) {
+  constexpr int NT = YM_W * YM_G, BW = YM_BW;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = align128(smem_raw);
+  MarchRing ring;
+  ring.init(smem);
+  const int tid = threadIdx.x, lx = tid % YM_W, grp = tid / YM_W;
+  const int G = gridDim.x;
+  pdl_trigger();
+  PdlGate gate(dep_start, trace);
+  if (dep_start == 0) {  // (as in advec_cell_tma_kernel: the halo ring of the old buffers moves to the new ones)
+    gate.need(0);
+    ring_copy(d_old, d_new, nx, ny, pitch, 0, (int)blockIdx.x * NT + tid, G * NT);
+    ring_copy(e_old, e_new, nx, ny, pitch, 0, (int)blockIdx.x * NT + tid, G * NT);
+  }
+  auto issue_tile = [&](int stage, int2 xy) {
+    const int j0 = 1 + xy.x * YM_W, k0 = 1 + xy.y * YM_H;
+    ring.issue(M.m, stage, j0 - 2 + XOFF, k0 - 2 + 1);
+  };
+  // Tile table with FOUR entries, indexed by iteration: entry it%4 = the tile computed at iteration it.  With one barrier
+  // per iteration the scheduler can then run two iterations ahead of the readers (it writes entry (it+2)%4 while the
+  // leader reads (it+1)%4 and everybody reads it%4).
+  __shared__ int s_tile[4];
+  __shared__ int2 s_xy[4];
+  __shared__ int s_q[8];
+  TileQueue<YM_STAGES> queue(tickets, ntiles, order, s_tile, s_xy, s_q);
+  const bool sched = (tid == 32);
+  if (sched) queue.prime_all();  // entries 0 and 1
+  __syncthreads();
+  if (tid == 0 && s_tile[0] < ntiles) {
+    gate.need(s_tile[0]);
+    issue_tile(0, s_xy[0]);
+  }
+  const int smax = ny + 2;
+  for (int it = 0;; ++it) {
+    const int stage = it % YM_STAGES;
+    const int t = s_tile[it & 3];
+    if (t >= ntiles) break;
+    const int2 cur = s_xy[it & 3];
+    gate.need(t);
+    if (sched) queue.step((it + 2) & 3);
+    if (tid == 0) {  // the other stage was released by the barrier that ended iteration it-1
+      const int tn = s_tile[(it + 1) & 3];
+      if (tn < ntiles) {
+        gate.need(tn);
+        issue_tile((stage + 1) % YM_STAGES, s_xy[(it + 1) & 3]);
+      }
+    }
+    const int j0 = 1 + cur.x * YM_W, k0 = 1 + cur.y * YM_H;
+    const int j = j0 + lx, kA = k0 + grp * YM_R;
+    // vertexdy at kA-1 .. kA+5 (1-D, lower bound -1 -> index k+1; clamped for rows that are never used)
+    double vd[YM_R + 3];
+#pragma unroll
+    for (int i = 0; i < YM_R + 3; ++i) vd[i] = vertexd[clampi(kA - 1 + i, -1, smax) + 1];
+    ring.wait(stage, (uint32_t)((it / YM_STAGES) & 1));
+    const double* __restrict__ svol = ring.tile(stage, CA_VOLUME);
+    const double* __restrict__ sfx = ring.tile(stage, CA_VFX);
+    const double* __restrict__ sfy = ring.tile(stage, CA_VFY);
+    const double* __restrict__ sd = ring.tile(stage, CA_DENSITY1);
+    const double* __restrict__ se = ring.tile(stage, CA_ENERGY1);
+    if (j <= nx && kA <= smax) {
+      const int b0 = (grp * YM_R + 2) * BW + lx + 2;  // box position of cell (j, kA); cell (j, kA+i) at b0 + i*BW
+      // pre_vol of the cells kA-1 .. kA+YM_R (:189-193 / :207-209)
+      double pv[YM_R + 2];
+#pragma unroll
+      for (int i = 0; i < YM_R + 2; ++i) {
+        const int c = b0 + (i - 1) * BW;
+        if (SWEEP == 1) pv[i] = svol[c] + (sfy[c + BW] - sfy[c] + sfx[c + 1] - sfx[c]);
+        else            pv[i] = svol[c] + sfy[c + BW] - sfy[c];
+      }
+      // density / energy of the cells kA-2 .. kA+YM_R+1
+      double d[YM_R + 4], e[YM_R + 4];
+#pragma unroll
+      for (int i = 0; i < YM_R + 4; ++i) {
+        d[i] = sd[b0 + (i - 2) * BW];
+        e[i] = se[b0 + (i - 2) * BW];
+      }
+      // the faces kA .. kA+YM_R (face k = lower face of cell k): :219-263
+      double mf[YM_R + 1], ef[YM_R + 1], vf[YM_R + 1];
+#pragma unroll
+      for (int f = 0; f <= YM_R; ++f) {
+        const int kf = kA + f;
+        mf[f] = 0.0; ef[f] = 0.0; vf[f] = 0.0;
+        if (kf <= smax) {
+          vf[f] = sfy[b0 + f * BW];
+          const bool pos = vf[f] > 0.0;
+          const bool up_ok = kf + 1 <= smax;  // MIN(k+1, y_max+2)
+          // cell kf is d[f+2]: upwind kf-2 | min(kf+1, ny+2), donor kf-1 | kf, downwind kf | kf-1
+          const double d_up = pos ? d[f] : (up_ok ? d[f + 3] : d[f + 2]);
+          const double e_up = pos ? e[f] : (up_ok ? e[f + 3] : e[f + 2]);
+          const double vdd = pos ? vd[f] : (up_ok ? vd[f + 2] : vd[f + 1]);  // vd[i] = vertexdy(kA-1+i)
+          cell_face_flux(vf[f], pos ? pv[f] : pv[f + 1], d_up, pos ? d[f + 1] : d[f + 2], pos ? d[f + 2] : d[f + 1], e_up,
+                         pos ? e[f + 1] : e[f + 2], pos ? e[f + 2] : e[f + 1], vd[f + 1], vdd, mf[f], ef[f]);
+          if (f < YM_R) mass_flux[idx2(pitch, j, kf)] = mf[f];  // own faces; the face on top belongs to the group above
+        }
+      }
+      // the cells kA .. kA+YM_R-1: :266-286
+#pragma unroll
+      for (int r = 0; r < YM_R; ++r) {
+        const int k = kA + r;
+        if (k <= ny) {
+          const double pre_mass = d[r + 2] * pv[r + 1];
+          const double post_mass = pre_mass + mf[r] - mf[r + 1];
+          const double post_ener = (e[r + 2] * pre_mass + ef[r] - ef[r + 1]) / post_mass;
+          const double advec_vol = pv[r + 1] + vf[r] - vf[r + 1];
+          const size_t o = idx2(pitch, j, k);
+          d_new[o] = post_mass / advec_vol;
+          e_new[o] = post_ener;
+        }
+      }
+    }
+    __syncthreads();  // the stage is free again
+  }
+  gate.finish();
+  if (sched) queue.leave();
+  if (dep_start != 0) {
+    ring_copy(d_old, d_new, nx, ny, pitch, 0, (int)blockIdx.x * NT + tid, G * NT);
+    ring_copy(e_old, e_new, nx, ny, pitch, 0, (int)blockIdx.x * NT + tid, G * NT);
+  }
+}
+
+template <int SWEEP>
+static void launch_cell_ymarch(const Grid& g, const CellMaps& M, const double* d_old, double* d_new, const double* e_old,
+                               double* e_new, double* mass_flux, const double* vertexd) {
+  static bool configured = false;
+  if (!configured) {
+    CLV_CUDA(cudaFuncSetAttribute(advec_cell_ymarch_tma_kernel<SWEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, YM_SMEM));
+    configured = true;
+  }
+  const int ntx = (g.nx + YM_W - 1) / YM_W, nty = (g.ny + 2 + YM_H - 1) / YM_H;  // rows 1 .. ny+2 (faces up to y_max+2)
+  const int ntiles = ntx * nty;
+  const int cap = sm_count() * 2;
+  const int ctas = ntiles < cap ? ntiles : cap;
+  const TileOrder ord = tile_order_split(ntx, nty, YM_W, YM_H, 2, YM_BW - 2 - YM_W, 2, YM_BH - 2 - YM_H, g.nx, g.ny);
+  launch_pdl(advec_cell_ymarch_tma_kernel<SWEEP>, dim3(ctas), dim3(YM_W * YM_G), YM_SMEM, stream(), M, d_old, d_new, e_old, e_new,
+             mass_flux, vertexd, g.nx, g.ny, g.pitch, ntiles, ord.table, next_tickets(), dep_start_for(ord), current_trace());
+}
+static bool ymarch_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("CLOVER_B200_YMARCH") ? atoi(getenv("CLOVER_B200_YMARCH")) : 1;  // 0: the three-phase kernel (A/B)
+  return v != 0;
+}
+
 void run_advec_cell_tma(const Grid& g, int dir, int sweep, double* vertexdx, double* vertexdy, double* volume,
                         double* density1, double* energy1, double* mass_flux_x, double* vol_flux_x, double* mass_flux_y,
                         double* vol_flux_y) {
@@ -516,8 +679,15 @@ void run_advec_cell_tma(const Grid& g, int dir, int sweep, double* vertexdx, dou
   // <thread grid TX x TY, rows per thread, ring stages, CTAs per SM>; measured on B200 at 3840^2:
   //   x: <64,4,2,2,3> 0.181 ms, <64,4,2,2,2> 0.221, <64,4,2,3,2> 0.224, <64,4,1,2,4> 0.236, <64,8,1,2,2> 0.236
   //   y: <32,8,2,2,3> 0.211 ms, <32,8,3,2,2> 0.217, <32,8,2,2,2> 0.247, <64,4,3,2,2> 0.245, <32,8,4,2,2> 0.342
-  if (dir == 1) CLV_CELL(1, 64, 4, 2, 2, 3);
-  else          CLV_CELL(2, 32, 8, 2, 2, 3);
+  if (dir == 1) {
+    CLV_CELL(1, 64, 4, 2, 2, 3);
+  } else if (ymarch_enabled()) {
+    for (int a = 0; a < CA_NARR; ++a) M.m[a] = *tensor_map_for(g, in[a], YM_BW, YM_BH);
+    if (sweep == 1) launch_cell_ymarch<1>(g, M, d_old, d_new, e_old, e_new, mf, vd);
+    else            launch_cell_ymarch<2>(g, M, d_old, d_new, e_old, e_new, mf, vd);
+  } else {
+    CLV_CELL(2, 32, 8, 2, 2, 3);
+  }
 #undef CLV_CELL
   swap_alt(density1);
   swap_alt(energy1);

@@ -1,5 +1,5 @@
 #!/bin/bash
-B="python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-e2e --active-skip 0"
-$B > gpurun_out/r3h_main.json 2> gpurun_out/r3h_main.err
-for v in q8 tt3 pt3 q2; do CLOVER_B200_LIB=$PWD/cloverleaf_b200/libclover_b200_$v.so $B > gpurun_out/r3h_$v.json 2> gpurun_out/r3h_$v.err; done
-$B > gpurun_out/r3h_main2.json 2> gpurun_out/r3h_main2.err
+CLOVER_B200_YMARCH=1 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/r3j_tests.log
+B="python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-e2e"
+$B > gpurun_out/r3j_main.json 2> gpurun_out/r3j_main.err
+CLOVER_B200_YMARCH=1 $B > gpurun_out/r3j_march.json 2> gpurun_out/r3j_march.err
