@@ -680,6 +680,8 @@ void run_advec_cell_tma(const Grid& g, int dir, int sweep, double* vertexdx, dou
   //   x: <64,4,2,2,3> 0.181 ms, <64,4,2,2,2> 0.221, <64,4,2,3,2> 0.224, <64,4,1,2,4> 0.236, <64,8,1,2,2> 0.236
   //   y: <32,8,2,2,3> 0.211 ms, <32,8,3,2,2> 0.217, <32,8,2,2,2> 0.247, <64,4,3,2,2> 0.245, <32,8,4,2,2> 0.342
   if (dir == 1) {
+    // (a barrier-free x variant -- a warp per row segment, the fluxes of face j+1 by warp shuffle, 30-wide tiles -- was
+    // bit-identical but slower: 0.187 vs 0.178 ms, profiles/r02_experiment_xrow.json)
     CLV_CELL(1, 64, 4, 2, 2, 3);
   } else if (ymarch_enabled()) {
     for (int a = 0; a < CA_NARR; ++a) M.m[a] = *tensor_map_for(g, in[a], YM_BW, YM_BH);
