@@ -276,6 +276,177 @@ static void launch_mom(const Grid& g, const MomMaps& M, const double* va_old, do
 }
 
 // ====================================================================================================================
+// advec_mom, y sweep, "column march" (see advec_cell_ymarch_tma_kernel below for the idea): thread (lx, grp) owns node
+// column j0+lx and the MM_R nodes k0+grp*MM_R .. of a 32 x (8*MM_R) tile.  Node fluxes, node masses, the MM_R+1 limited
+// momentum fluxes and the MM_R velocity updates of a thread all come from its own column (and column j-1) of the staged
+// boxes; nothing travels between threads, so there are no planes and no barriers between phases.  The flux through the
+// node face under a group is evaluated twice (once by the group below) instead of handed over behind a barrier.
+// Boxes: columns j0-2 .. j0+33, rows k0-2 .. k0+H+1.  MM_R = 3 keeps the six-box ring at two CTAs per SM.
+constexpr int MM_R = 3, MM_G = 8, MM_W = 32, MM_H = MM_G * MM_R, MM_BW = MM_W + 4, MM_BH = MM_H + 4, MM_STAGES = 2;
+using MomMarchRing = TileRing<MA_NARR, MM_BW, MM_BH, MM_STAGES>;
+constexpr int MM_SMEM = MomMarchRing::BYTES + 128;
+
+template <int MS>  // mom_sweep 2 (first sweep along y) or 4 (second sweep along y)
+__global__ void __launch_bounds__(MM_W* MM_G, 2)
+    advec_mom_ymarch_tma_kernel(const __grid_constant__ MomMaps M, const double* __restrict__ va_old, double* __restrict__ va_new,
+                                const double* __restrict__ vb_old, double* __restrict__ vb_new,
+                                const double* __restrict__ celld, int nx, int ny, int pitch, int ntiles,
+                                const int2* __restrict__ order, Tickets tickets, int dep_start, unsigned long long* trace) {
+  constexpr int NT = MM_W * MM_G, BW = MM_BW, R = MM_R;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = align128(smem_raw);
+  MomMarchRing ring;
+  ring.init(smem);
+  const int tid = threadIdx.x, lx = tid % MM_W, grp = tid / MM_W;
+  const int G = gridDim.x;
+  pdl_trigger();
+  PdlGate gate(dep_start, trace);
+  if (dep_start == 0) {
+    gate.need(0);
+    ring_copy(va_old, va_new, nx, ny, pitch, 1, (int)blockIdx.x * NT + tid, G * NT);
+    ring_copy(vb_old, vb_new, nx, ny, pitch, 1, (int)blockIdx.x * NT + tid, G * NT);
+  }
+  auto issue_tile = [&](int stage, int2 xy) {
+    const int j0 = 1 + xy.x * MM_W, k0 = 1 + xy.y * MM_H;
+    ring.issue(M.m, stage, j0 - 2 + XOFF, k0 - 2 + 1);
+  };
+  __shared__ int s_tile[4];  // four entries indexed by iteration (see advec_cell_ymarch_tma_kernel)
+  __shared__ int2 s_xy[4];
+  __shared__ int s_q[8];
+  TileQueue<MM_STAGES> queue(tickets, ntiles, order, s_tile, s_xy, s_q);
+  const bool sched = (tid == 32);
+  if (sched) queue.prime_all();
+  __syncthreads();
+  if (tid == 0 && s_tile[0] < ntiles) {
+    gate.need(s_tile[0]);
+    issue_tile(0, s_xy[0]);
+  }
+  const int smax = ny + 2;
+  for (int it = 0;; ++it) {
+    const int stage = it % MM_STAGES;
+    const int t = s_tile[it & 3];
+    if (t >= ntiles) break;
+    const int2 cur = s_xy[it & 3];
+    gate.need(t);
+    if (sched) queue.step((it + 2) & 3);
+    if (tid == 0) {
+      const int tn = s_tile[(it + 1) & 3];
+      if (tn < ntiles) {
+        gate.need(tn);
+        issue_tile((stage + 1) % MM_STAGES, s_xy[(it + 1) & 3]);
+      }
+    }
+    const int j0 = 1 + cur.x * MM_W, k0 = 1 + cur.y * MM_H;
+    const int j = j0 + lx, kA = k0 + grp * R;
+    // celldy at kA-2 .. kA+R (1-D, lower bound -1 -> index k+1; clamped for rows that are never used)
+    double cd[R + 3];
+#pragma unroll
+    for (int i = 0; i < R + 3; ++i) cd[i] = celld[clampi(kA - 2 + i, -1, smax) + 1];
+    ring.wait(stage, (uint32_t)((it / MM_STAGES) & 1));
+    const double* __restrict__ svol = ring.tile(stage, MA_VOLUME);
+    const double* __restrict__ sd1 = ring.tile(stage, MA_DENSITY1);
+    const double* __restrict__ smf = ring.tile(stage, MA_MASS_FLUX);
+    const double* __restrict__ sva = ring.tile(stage, MA_VEL_A);
+    const double* __restrict__ svb = ring.tile(stage, MA_VEL_B);
+    const double* __restrict__ svf = ring.tile(stage, MA_VOL_FLUX);
+    if (j <= nx + 1 && kA <= ny + 1) {
+      const int bA = (grp * R + 2) * BW + lx + 2;  // box position of (j, kA); (j, kA+i) at bA + i*BW
+      auto pm = [&](int c) {                       // post_vol * density1 of a cell (:69-121)
+        const double post_vol = (MS == 2) ? svol[c] + svf[c + 1] - svf[c] : svol[c];
+        return sd1[c] * post_vol;
+      };
+      // node_mass_post of the nodes kA-1 .. kA+R (:216-231): cells (j,k-1)+(j,k)+(j-1,k-1)+(j-1,k)
+      double np[R + 2];
+      {
+        double pmR[R + 3], pmL[R + 3];
+#pragma unroll
+        for (int i = 0; i < R + 3; ++i) {
+          pmR[i] = pm(bA + (i - 2) * BW);
+          pmL[i] = pm(bA + (i - 2) * BW - 1);
+        }
+#pragma unroll
+        for (int i = 0; i < R + 2; ++i) np[i] = 0.25 * (pmR[i] + pmR[i + 1] + pmL[i] + pmL[i + 1]);
+      }
+      // node_flux of the nodes kA-2 .. kA+R (:205-214): mass_flux_y (j-1,k)+(j,k)+(j-1,k+1)+(j,k+1)
+      double nf[R + 3];
+      {
+        double m0[R + 4], m1[R + 4];
+#pragma unroll
+        for (int i = 0; i < R + 4; ++i) {
+          m0[i] = smf[bA + (i - 2) * BW - 1];
+          m1[i] = smf[bA + (i - 2) * BW];
+        }
+#pragma unroll
+        for (int i = 0; i < R + 3; ++i) nf[i] = 0.25 * (m0[i] + m1[i] + m0[i + 1] + m1[i + 1]);
+      }
+      // velocities at kA-2 .. kA+R+1
+      double va[R + 4], vb[R + 4];
+#pragma unroll
+      for (int i = 0; i < R + 4; ++i) {
+        va[i] = sva[bA + (i - 2) * BW];
+        vb[i] = svb[bA + (i - 2) * BW];
+      }
+      // the momentum fluxes through the node faces kA-1 .. kA+R-1 (:240-270); face kf <-> nf[f+1], np[f], cd[f+1]
+      double ma[R + 1], mb[R + 1], nmpre[R + 1];
+#pragma unroll
+      for (int f = 0; f <= R; ++f) {
+        const double fl = nf[f + 1], f_m = nf[f], f_p = nf[f + 2];
+        nmpre[f] = np[f] - f_m + fl;
+        const double nm_pre_p = np[f + 1] - fl + f_p;
+        const bool neg = fl < 0.0;
+        const double width = cd[f + 1], width_dif = neg ? cd[f + 2] : cd[f];
+        const double nmp_don = neg ? nm_pre_p : nmpre[f];
+        ma[f] = 0.0;
+        mb[f] = 0.0;
+        if (kA - 1 + f <= ny + 1) {
+          ma[f] = mom_face_flux(fl, nmp_don, neg ? va[f + 3] : va[f], neg ? va[f + 2] : va[f + 1], neg ? va[f + 1] : va[f + 2], width, width_dif);
+          mb[f] = mom_face_flux(fl, nmp_don, neg ? vb[f + 3] : vb[f], neg ? vb[f + 2] : vb[f + 1], neg ? vb[f + 1] : vb[f + 2], width, width_dif);
+        }
+      }
+      // the nodes kA .. kA+R-1 (:272-282)
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int k = kA + r;
+        if (k <= ny + 1) {
+          const size_t o = idx2(pitch, j, k);
+          va_new[o] = ddiv(va[r + 2] * nmpre[r + 1] + ma[r] - ma[r + 1], np[r + 1]);
+          vb_new[o] = ddiv(vb[r + 2] * nmpre[r + 1] + mb[r] - mb[r + 1], np[r + 1]);
+        }
+      }
+    }
+    __syncthreads();  // the stage is free again
+  }
+  gate.finish();
+  if (sched) queue.leave();
+  if (dep_start != 0) {
+    ring_copy(va_old, va_new, nx, ny, pitch, 1, (int)blockIdx.x * NT + tid, G * NT);
+    ring_copy(vb_old, vb_new, nx, ny, pitch, 1, (int)blockIdx.x * NT + tid, G * NT);
+  }
+}
+
+template <int MS>
+static void launch_mom_ymarch(const Grid& g, const MomMaps& M, const double* va_old, double* va_new, const double* vb_old,
+                              double* vb_new, const double* celld) {
+  static bool configured = false;
+  if (!configured) {
+    CLV_CUDA(cudaFuncSetAttribute(advec_mom_ymarch_tma_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM));
+    configured = true;
+  }
+  const int ntx = (g.nx + 1 + MM_W - 1) / MM_W, nty = (g.ny + 1 + MM_H - 1) / MM_H;
+  const int ntiles = ntx * nty;
+  const int cap = sm_count() * 2;
+  const int ctas = ntiles < cap ? ntiles : cap;
+  const TileOrder ord = tile_order_split(ntx, nty, MM_W, MM_H, 2, MM_BW - 2 - MM_W, 2, MM_BH - 2 - MM_H, g.nx, g.ny);
+  launch_pdl(advec_mom_ymarch_tma_kernel<MS>, dim3(ctas), dim3(MM_W * MM_G), MM_SMEM, stream(), M, va_old, va_new, vb_old, vb_new,
+             celld, g.nx, g.ny, g.pitch, ntiles, ord.table, next_tickets(), dep_start_for(ord), current_trace());
+}
+static bool mom_ymarch_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("CLOVER_B200_MOM_YMARCH") ? atoi(getenv("CLOVER_B200_MOM_YMARCH")) : 1;  // 0: the three-phase kernel (A/B)
+  return v != 0;
+}
+
+// ====================================================================================================================
 // advec_cell (advec_cell_kernel_c.c:72-177 x sweep, :182-290 y sweep).  `s` is the sweep axis, the tile owns the cells
 // s0 .. s0+NS-1 and the thread grid has N = NS+3(+1) positions along the sweep, position i <-> index s0-1+i:
 //   A  pre_vol(s)                   all positions                  (:72-102 / :182-214)
@@ -725,8 +896,15 @@ void run_advec_mom_tma(const Grid& g, int dirn, int sweep, double* vel_a, double
   // <thread grid TX x TY, rows per thread, ring stages, CTAs per SM>; measured on B200 at 3840^2:
   //   x: <64,4,2,2,2> 0.211 ms, <64,4,1,2,4> 0.216, <64,8,1,2,2> 0.221, <64,4,2,3,2> 0.229, <64,2,4,2,2> 0.305
   //   y: <32,8,3,2,2> 0.214 ms, <32,8,2,2,3> 0.236, <32,4,4,2,3> 0.240, <32,8,2,2,2> 0.247, <32,16,1,2,2> 0.255
-  if (dirn == 1) CLV_MOM(1, 64, 4, 2, 2, 2);
-  else           CLV_MOM(2, 32, 8, 3, 2, 2);
+  if (dirn == 1) {
+    CLV_MOM(1, 64, 4, 2, 2, 2);
+  } else if (mom_ymarch_enabled()) {
+    for (int a = 0; a < MA_NARR; ++a) M.m[a] = *tensor_map_for(g, in[a], MM_BW, MM_BH);
+    if (mom_sweep == 2) launch_mom_ymarch<2>(g, M, va_old, va_new, vb_old, vb_new, cd);
+    else                launch_mom_ymarch<4>(g, M, va_old, va_new, vb_old, vb_new, cd);
+  } else {
+    CLV_MOM(2, 32, 8, 3, 2, 2);
+  }
 #undef CLV_MOM
   swap_alt(vel_a);
   swap_alt(vel_b);
