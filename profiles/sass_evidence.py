@@ -13,6 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "cloverleaf_b200", "libclover_b200.so")
 KERNELS = ["timestep_tma_kernel", "pdv_predict_eos_tma_kernel", "lagrange_correct_tma_kernel", "advec_cell_tma_kernel",
+           "advec_cell_ymarch_tma_kernel", "advec_mom_ymarch_tma_kernel",
            "advec_mom_tma_kernel", "halo_exchange_kernel", "update_halo_kernel"]
 MNEMONICS = ["UTMALDG", "SYNCS.ARRIVE", "SYNCS.PHASECHK", "SYNCS.EXCH", "ACQBULK", "ATOMG", "LDS", "STS", "LDG", "STG", "DFMA",
              "DMUL", "DADD", "MUFU", "BAR.SYNC", "LDC", "MEMBAR", "ELECT"]
