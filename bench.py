@@ -48,7 +48,9 @@ KERNEL_PASSES = {
     "revert": (4, 4), "accelerate": (10, 10), "flux_calc": (8, 8), "reset_field": (8, 8), "field_summary": (6, 6),
     "advec_cell_x": (7.5, 7.5), "advec_cell_y": (7.5, 7.5), "advec_cell_x_tma": (7.5, 7.5), "advec_cell_y_tma": (7.5, 7.5),
     "advec_mom_x": (4.25, 4.25), "advec_mom_y": (4.25, 4.25), "advec_mom_x2": (8.5, 8.5), "advec_mom_y2": (8.5, 8.5),
-    "advec_mom_x_tma": (8.5, 8.5), "advec_mom_y_tma": (8.5, 8.5),
+    # both velocity components per launch: reads volume, density1, mass_flux, 2 velocities (+ one volume flux in the
+    # first sweep of a step only: mom_sweep 1 / 2), writes 2 velocities -> 8 and 7 passes, one launch of each per step
+    "advec_mom_x_tma": (7.5, 8.5), "advec_mom_y_tma": (7.5, 8.5),
     # fused launches (csrc/fuse.cu): ideal_gas+viscosity+calc_dt reads d0,e0,u0,v0,volume,xarea,yarea and writes p,q
     # (the TMA variant leaves the sound speed unevaluated: nothing reads it before it is overwritten; the register variant writes it);
     # PdV predictor+ideal_gas+revert reads 9 fields and writes p; accelerate+PdV corrector+flux_calc reads 9, writes 6

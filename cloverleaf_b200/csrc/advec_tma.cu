@@ -47,7 +47,11 @@ __device__ __forceinline__ void ring_copy(const double* __restrict__ src, double
 
 enum { MA_VOLUME = 0, MA_DENSITY1, MA_MASS_FLUX, MA_VEL_A, MA_VEL_B, MA_VOL_FLUX, MA_NARR };
 
-template <int DIR, int TX, int TY, int RPT, int STAGES, int CPS>
+// boxes a sweep stages: the post-volume of mom_sweep 1 / 2 needs a volume flux (:69-121), that of 3 / 4 does not --
+// the sixth box is then neither loaded nor given room (one of 8.5 passes less: these launches are DRAM-heavy)
+constexpr int mom_narr(int ms) { return ms <= 2 ? MA_NARR : MA_NARR - 1; }
+
+template <int DIR, int TX, int TY, int RPT, int STAGES, int CPS, int MS = 1>
 struct MomCfg {
   static constexpr int NT = TX * TY;
   static constexpr int ROWS = TY * RPT;
@@ -56,7 +60,7 @@ struct MomCfg {
   static constexpr int BW = DIR == 1 ? TX : TX + 4;         // box: x from j0-2
   static constexpr int BH = DIR == 1 ? H + 2 : H + 4;       // box: y from k0-1 (x sweep) / k0-2 (y sweep)
   static constexpr int OX = 2, OY = DIR == 1 ? 1 : 2;
-  using Ring = TileRing<MA_NARR, BW, BH, STAGES>;
+  using Ring = TileRing<mom_narr(MS), BW, BH, STAGES>;
   static constexpr int NI = TX * ROWS;                      // one intermediate plane: thread-grid shaped
   static constexpr int SMEM = Ring::BYTES + 4 * NI * 8 + 128;
 };
@@ -71,7 +75,7 @@ __global__ void __launch_bounds__(TX* TY, CPS)
                          const double* __restrict__ vb_old, double* __restrict__ vb_new,
                          const double* __restrict__ celld, int nx, int ny, int pitch, int ntx, int ntiles,
                         const int2* __restrict__ order, Tickets tickets, int dep_start, unsigned long long* trace) {
-  using Cfg = MomCfg<DIR, TX, TY, RPT, STAGES, CPS>;
+  using Cfg = MomCfg<DIR, TX, TY, RPT, STAGES, CPS, MS>;
   constexpr int NT = Cfg::NT, W = Cfg::W, H = Cfg::H, BW = Cfg::BW, NI = Cfg::NI, OX = Cfg::OX, OY = Cfg::OY;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = align128(smem_raw);
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(TX* TY, CPS)
     const double* __restrict__ smf = ring.tile(stage, MA_MASS_FLUX);
     const double* __restrict__ sva = ring.tile(stage, MA_VEL_A);
     const double* __restrict__ svb = ring.tile(stage, MA_VEL_B);
-    const double* __restrict__ svf = ring.tile(stage, MA_VOL_FLUX);
+    const double* __restrict__ svf = ring.tile(stage, MS <= 2 ? MA_VOL_FLUX : MA_VOLUME);  // (read for MS 1 / 2 only)
     // Thread (lx, ty) owns the RPT adjacent plane rows ty*RPT + r, plane position p = row*TX + lx.
     // x sweep: plane column lx <-> node j0-2+lx, plane row <-> node k0+row.
     // y sweep: plane column lx <-> node j0+lx,   plane row <-> node k0-2+row.
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(TX* TY, CPS)
 template <int DIR, int MS, int TX, int TY, int RPT, int STAGES, int CPS>
 static void launch_mom(const Grid& g, const MomMaps& M, const double* va_old, double* va_new, const double* vb_old,
                        double* vb_new, const double* celld) {
-  using Cfg = MomCfg<DIR, TX, TY, RPT, STAGES, CPS>;
+  using Cfg = MomCfg<DIR, TX, TY, RPT, STAGES, CPS, MS>;
   static bool configured = false;
   if (!configured) {
     CLV_CUDA(cudaFuncSetAttribute(advec_mom_tma_kernel<DIR, MS, TX, TY, RPT, STAGES, CPS>,
@@ -283,8 +287,10 @@ static void launch_mom(const Grid& g, const MomMaps& M, const double* va_old, do
 // node face under a group is evaluated twice (once by the group below) instead of handed over behind a barrier.
 // Boxes: columns j0-2 .. j0+33, rows k0-2 .. k0+H+1.  MM_R = 3 keeps the six-box ring at two CTAs per SM.
 constexpr int MM_R = 3, MM_G = 8, MM_W = 32, MM_H = MM_G * MM_R, MM_BW = MM_W + 4, MM_BH = MM_H + 4, MM_STAGES = 2;
-using MomMarchRing = TileRing<MA_NARR, MM_BW, MM_BH, MM_STAGES>;
-constexpr int MM_SMEM = MomMarchRing::BYTES + 128;
+template <int MS>
+using MomMarchRing = TileRing<mom_narr(MS), MM_BW, MM_BH, MM_STAGES>;
+template <int MS>
+constexpr int mm_smem() { return MomMarchRing<MS>::BYTES + 128; }
 
 template <int MS>  // mom_sweep 2 (first sweep along y) or 4 (second sweep along y)
 __global__ void __launch_bounds__(MM_W* MM_G, 2)
@@ -295,7 +301,7 @@ __global__ void __launch_bounds__(MM_W* MM_G, 2)
   constexpr int NT = MM_W * MM_G, BW = MM_BW, R = MM_R;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = align128(smem_raw);
-  MomMarchRing ring;
+  MomMarchRing<MS> ring;
   ring.init(smem);
   const int tid = threadIdx.x, lx = tid % MM_W, grp = tid / MM_W;
   const int G = gridDim.x;
@@ -348,7 +354,7 @@ __global__ void __launch_bounds__(MM_W* MM_G, 2)
     const double* __restrict__ smf = ring.tile(stage, MA_MASS_FLUX);
     const double* __restrict__ sva = ring.tile(stage, MA_VEL_A);
     const double* __restrict__ svb = ring.tile(stage, MA_VEL_B);
-    const double* __restrict__ svf = ring.tile(stage, MA_VOL_FLUX);
+    const double* __restrict__ svf = ring.tile(stage, MS <= 2 ? MA_VOL_FLUX : MA_VOLUME);  // (read for MS 2 only)
     if (j <= nx + 1 && kA <= ny + 1) {
       const int bA = (grp * R + 2) * BW + lx + 2;  // box position of (j, kA); (j, kA+i) at bA + i*BW
       auto pm = [&](int c) {                       // post_vol * density1 of a cell (:69-121)
@@ -429,7 +435,7 @@ static void launch_mom_ymarch(const Grid& g, const MomMaps& M, const double* va_
                               double* vb_new, const double* celld) {
   static bool configured = false;
   if (!configured) {
-    CLV_CUDA(cudaFuncSetAttribute(advec_mom_ymarch_tma_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM));
+    CLV_CUDA(cudaFuncSetAttribute(advec_mom_ymarch_tma_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, mm_smem<MS>()));
     configured = true;
   }
   const int ntx = (g.nx + 1 + MM_W - 1) / MM_W, nty = (g.ny + 1 + MM_H - 1) / MM_H;
@@ -437,7 +443,7 @@ static void launch_mom_ymarch(const Grid& g, const MomMaps& M, const double* va_
   const int cap = sm_count() * 2;
   const int ctas = ntiles < cap ? ntiles : cap;
   const TileOrder ord = tile_order_split(ntx, nty, MM_W, MM_H, 2, MM_BW - 2 - MM_W, 2, MM_BH - 2 - MM_H, g.nx, g.ny);
-  launch_pdl(advec_mom_ymarch_tma_kernel<MS>, dim3(ctas), dim3(MM_W * MM_G), MM_SMEM, stream(), M, va_old, va_new, vb_old, vb_new,
+  launch_pdl(advec_mom_ymarch_tma_kernel<MS>, dim3(ctas), dim3(MM_W * MM_G), mm_smem<MS>(), stream(), M, va_old, va_new, vb_old, vb_new,
              celld, g.nx, g.ny, g.pitch, ntiles, ord.table, next_tickets(), dep_start_for(ord), current_trace());
 }
 static bool mom_ymarch_enabled() {

@@ -36,4 +36,4 @@ def test_fused_step_adds_up_to_the_survey_figure():
     survey = sum(P[k][1] for k in step) + P["reset_field"][1]
     assert survey == 107 and survey * 8 == bench.ALG_BYTES_PER_CELL_STEP
     own = sum(P[k][0] for k in step)
-    assert own == 66  # 528 B per cell-update actually moved (the sound speed is never stored)
+    assert own == 64  # 512 B per cell-update actually moved (the sound speed is never stored)
