@@ -62,7 +62,9 @@ struct MomCfg {
   static constexpr int OX = 2, OY = DIR == 1 ? 1 : 2;
   using Ring = TileRing<mom_narr(MS), BW, BH, STAGES>;
   static constexpr int NI = TX * ROWS;                      // one intermediate plane: thread-grid shaped
-  static constexpr int SMEM = Ring::BYTES + 4 * NI * 8 + 128;
+  // the two momentum-flux planes live in the volume / density1 boxes of the stage, dead after phase A
+  static_assert(NI <= BW * BH, "a plane must fit a box");
+  static constexpr int SMEM = Ring::BYTES + 2 * NI * 8 + 128;
 };
 struct MomMaps {
   CUtensorMap m[MA_NARR];
@@ -83,8 +85,6 @@ __global__ void __launch_bounds__(TX* TY, CPS)
   ring.init(smem);
   double* __restrict__ s_nf = reinterpret_cast<double*>(smem + Cfg::Ring::BYTES);  // node_flux
   double* __restrict__ s_np = s_nf + NI;                                           // node_mass_post
-  double* __restrict__ s_ma = s_np + NI;                                           // mom_flux, component a
-  double* __restrict__ s_mb = s_ma + NI;                                           // mom_flux, component b
   const int tid = threadIdx.x, lx = tid % TX, ty = tid / TX;
   const int G = gridDim.x;
   pdl_trigger();
@@ -149,8 +149,10 @@ __global__ void __launch_bounds__(TX* TY, CPS)
       }
     }
     ring.wait(stage, (uint32_t)((it / STAGES) & 1));
-    const double* __restrict__ svol = ring.tile(stage, MA_VOLUME);
-    const double* __restrict__ sd1 = ring.tile(stage, MA_DENSITY1);
+    const double* svol = ring.tile(stage, MA_VOLUME);
+    const double* sd1 = ring.tile(stage, MA_DENSITY1);
+    double* s_ma = ring.scratch(stage, MA_VOLUME);   // mom_flux, component a: written after the barrier that ends phase A,
+    double* s_mb = ring.scratch(stage, MA_DENSITY1);  // component b            the last reader of these two boxes
     const double* __restrict__ smf = ring.tile(stage, MA_MASS_FLUX);
     const double* __restrict__ sva = ring.tile(stage, MA_VEL_A);
     const double* __restrict__ svb = ring.tile(stage, MA_VEL_B);
@@ -888,7 +890,7 @@ void run_advec_mom_tma(const Grid& g, int dirn, int sweep, double* vel_a, double
   const double* mf = dirn == 1 ? dev(g, mass_flux_x, XFACE, IN) : dev(g, mass_flux_y, YFACE, IN);
   const double* cd = dirn == 1 ? dev(g, celldx, X1D_CELL, IN) : dev(g, celldy, Y1D_CELL, IN);
   // the post-volume of mom_sweep 1 needs vol_flux_y, of mom_sweep 2 vol_flux_x, of 3 and 4 neither (:69-121);
-  // the sixth box of sweeps 3/4 is loaded but never read
+  // the sixth box of sweeps 3/4 is neither mapped into the ring nor loaded (mom_narr)
   const double* in[MA_NARR] = {vol, d1, mf, va_old, vb_old, mom_sweep == 1 ? fy : fx};
   MomMaps M;
   LaunchScope ls(dirn == 1 ? "advec_mom_x_tma" : "advec_mom_y_tma");
@@ -903,7 +905,7 @@ void run_advec_mom_tma(const Grid& g, int dirn, int sweep, double* vel_a, double
   //   x: <64,4,2,2,2> 0.211 ms, <64,4,1,2,4> 0.216, <64,8,1,2,2> 0.221, <64,4,2,3,2> 0.229, <64,2,4,2,2> 0.305
   //   y: <32,8,3,2,2> 0.214 ms, <32,8,2,2,3> 0.236, <32,4,4,2,3> 0.240, <32,8,2,2,2> 0.247, <32,16,1,2,2> 0.255
   if (dirn == 1) {
-    CLV_MOM(1, 64, 4, 2, 2, 2);
+    CLV_MOM(1, 64, 4, 2, 2, 3);
   } else if (mom_ymarch_enabled()) {
     for (int a = 0; a < MA_NARR; ++a) M.m[a] = *tensor_map_for(g, in[a], MM_BW, MM_BH);
     if (mom_sweep == 2) launch_mom_ymarch<2>(g, M, va_old, va_new, vb_old, vb_new, cd);

@@ -115,6 +115,10 @@ struct TileRing {
   __device__ __forceinline__ const double* tile(int stage, int a) const {
     return reinterpret_cast<const double*>(base + stage * STAGE_BYTES + a * ARR_BYTES);
   }
+  // a box whose contents are dead, reused as scratch until the stage is issued again (issue() fences the proxies)
+  __device__ __forceinline__ double* scratch(int stage, int a) const {
+    return reinterpret_cast<double*>(base + stage * STAGE_BYTES + a * ARR_BYTES);
+  }
   // one thread: load the boxes with corner (x, y) of all NARR maps into `stage`
   // (x must be even, see the header comment)
   __device__ __forceinline__ void issue(const CUtensorMap* maps, int stage, int x, int y) {
