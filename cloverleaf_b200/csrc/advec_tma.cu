@@ -462,9 +462,18 @@ static bool mom_ymarch_enabled() {
 //   C  density1(s), energy1(s)      positions 1 .. NS                                      (:156-175 / :266-286)
 // mass_flux is stored for the faces of the tile's own cells; the last tile along the sweep also stores the faces
 // n+1 and n+2 (the loop of the reference runs to x_max+2 / y_max+2).
-enum { CA_VOLUME = 0, CA_VFX, CA_VFY, CA_DENSITY1, CA_ENERGY1, CA_NARR };
+// Boxes: CA_VF is the volume flux along the sweep, CA_VFC the one across it.  Only the pre-volume of the first sweep of a
+// step reads the cross flux (:77-81 / :189-193 against :94-96 / :207-209), so the second sweep neither loads that box
+// nor gives it room (one of eight passes less).
+// CTAs per SM of the x sweep: with the flux planes inside dead boxes four fit, but 64 registers spill (94 bytes) and
+// the launch is slower: 0.201 vs 0.178 ms (profiles/r02_experiment_occupancy.txt)
+#ifndef CELLX_CPS
+#define CELLX_CPS 3
+#endif
+enum { CA_VOLUME = 0, CA_VF, CA_DENSITY1, CA_ENERGY1, CA_VFC, CA_NARR };
+constexpr int cell_narr(int sweep) { return sweep == 1 ? CA_NARR : CA_NARR - 1; }
 
-template <int DIR, int TX, int TY, int RPT, int STAGES, int CPS>
+template <int DIR, int TX, int TY, int RPT, int STAGES, int CPS, int SWEEP = 1>
 struct CellCfg {
   static constexpr int NT = TX * TY;
   static constexpr int ROWS = TY * RPT;
@@ -473,9 +482,13 @@ struct CellCfg {
   static constexpr int BW = DIR == 1 ? TX + 2 : TX + 4; // box: x from j0-2
   static constexpr int BH = DIR == 1 ? ROWS + 1 : ROWS + 2;  // box: y from k0 (x sweep) / k0-2 (y sweep)
   static constexpr int OX = 2, OY = DIR == 1 ? 0 : 2;
-  using Ring = TileRing<CA_NARR, BW, BH, STAGES>;
+  using Ring = TileRing<cell_narr(SWEEP), BW, BH, STAGES>;
   static constexpr int NI = TX * ROWS;
-  static constexpr int SMEM = Ring::BYTES + 3 * NI * 8 + 128;
+  // planes of their own: pre_vol, and in the second sweep the energy flux; the mass flux lives in the volume box and the
+  // first sweep's energy flux in the cross-flux box, both dead once phase A is behind its barrier
+  static_assert(NI <= BW * BH, "a plane must fit a box");
+  static constexpr int NPLANES = SWEEP == 1 ? 1 : 2;
+  static constexpr int SMEM = Ring::BYTES + NPLANES * NI * 8 + 128;
 };
 struct CellMaps {
   CUtensorMap m[CA_NARR];
@@ -488,7 +501,7 @@ __global__ void __launch_bounds__(TX* TY, CPS)
                           double* __restrict__ mass_flux, const double* __restrict__ vertexd, int nx, int ny, int pitch,
                           int ntx, int nty, const int2* __restrict__ order, Tickets tickets, int dep_start,
                           unsigned long long* trace) {
-  using Cfg = CellCfg<DIR, TX, TY, RPT, STAGES, CPS>;
+  using Cfg = CellCfg<DIR, TX, TY, RPT, STAGES, CPS, SWEEP>;
   constexpr int NT = Cfg::NT, W = Cfg::W, H = Cfg::H, BW = Cfg::BW, NI = Cfg::NI, OX = Cfg::OX, OY = Cfg::OY;
   constexpr int NS = DIR == 1 ? W : H;             // cells of a tile along the sweep
   constexpr int NPS = DIR == 1 ? TX : Cfg::ROWS;   // plane positions along the sweep
@@ -497,8 +510,6 @@ __global__ void __launch_bounds__(TX* TY, CPS)
   typename Cfg::Ring ring;
   ring.init(smem);
   double* __restrict__ s_pv = reinterpret_cast<double*>(smem + Cfg::Ring::BYTES);  // pre_vol
-  double* __restrict__ s_mf = s_pv + NI;                                           // mass flux through the lower face
-  double* __restrict__ s_ef = s_mf + NI;                                           // energy flux
   const int tid = threadIdx.x, lx = tid % TX, ty = tid / TX;
   const int G = gridDim.x;
   const int ntiles = ntx * nty;
@@ -533,6 +544,7 @@ __global__ void __launch_bounds__(TX* TY, CPS)
     }
   }
   constexpr int SB = DIR == 1 ? 1 : BW;  // box stride along the sweep
+  constexpr int SC = DIR == 1 ? BW : 1;  // box stride across the sweep
   constexpr int SP = DIR == 1 ? 1 : TX;  // plane stride along the sweep
   const int smax = (DIR == 1 ? nx : ny) + 2;
   for (int it = 0;; ++it) {
@@ -564,12 +576,13 @@ __global__ void __launch_bounds__(TX* TY, CPS)
       vdu[r] = vertexd[clampi(sup, -1, smax) + 1];
     }
     ring.wait(stage, (uint32_t)((it / STAGES) & 1));
-    const double* __restrict__ svol = ring.tile(stage, CA_VOLUME);
-    const double* __restrict__ sfx = ring.tile(stage, CA_VFX);
-    const double* __restrict__ sfy = ring.tile(stage, CA_VFY);
+    const double* svol = ring.tile(stage, CA_VOLUME);
+    const double* __restrict__ svf = ring.tile(stage, CA_VF);        // the volume flux along the sweep
+    const double* svc = ring.tile(stage, SWEEP == 1 ? CA_VFC : CA_VOLUME);  // across it (read for SWEEP 1 only)
+    double* s_mf = ring.scratch(stage, CA_VOLUME);                   // mass flux through the lower face   (phases B, C)
+    double* s_ef = SWEEP == 1 ? ring.scratch(stage, CA_VFC) : s_pv + NI;  // energy flux                  (phases B, C)
     const double* __restrict__ sd = ring.tile(stage, CA_DENSITY1);
     const double* __restrict__ se = ring.tile(stage, CA_ENERGY1);
-    const double* __restrict__ svf = DIR == 1 ? sfx : sfy;  // the volume flux along the sweep
     // x sweep: plane column lx <-> cell j0-1+lx (box column lx+1), plane row <-> k0+row (box row row).
     // y sweep: plane column lx <-> cell j0+lx (box column lx+2),   plane row <-> k0-1+row (box row row+1).
     const int b0 = DIR == 1 ? row0 * BW + lx + 1 : (row0 + 1) * BW + lx + OX;
@@ -579,13 +592,9 @@ __global__ void __launch_bounds__(TX* TY, CPS)
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
       const int c = b0 + r * BW;
-      if (DIR == 1) {
-        if (SWEEP == 1) pv[r] = svol[c] + (sfx[c + 1] - sfx[c] + sfy[c + BW] - sfy[c]);  // :77-81
-        else            pv[r] = svol[c] + sfx[c + 1] - sfx[c];                            // :94-96
-      } else {
-        if (SWEEP == 1) pv[r] = svol[c] + (sfy[c + BW] - sfy[c] + sfx[c + 1] - sfx[c]);  // :189-193
-        else            pv[r] = svol[c] + sfy[c + BW] - sfy[c];                           // :207-209
-      }
+      // the flux difference along the sweep first, then the one across it: :77-81 / :189-193; sweep 2: :94-96 / :207-209
+      if (SWEEP == 1) pv[r] = svol[c] + (svf[c + SB] - svf[c] + svc[c + SC] - svc[c]);
+      else            pv[r] = svol[c] + svf[c + SB] - svf[c];
       s_pv[p0 + r * TX] = pv[r];
     }
     __syncthreads();
@@ -652,7 +661,7 @@ __global__ void __launch_bounds__(TX* TY, CPS)
 template <int DIR, int SWEEP, int TX, int TY, int RPT, int STAGES, int CPS>
 static void launch_cell(const Grid& g, const CellMaps& M, const double* d_old, double* d_new, const double* e_old,
                         double* e_new, double* mass_flux, const double* vertexd) {
-  using Cfg = CellCfg<DIR, TX, TY, RPT, STAGES, CPS>;
+  using Cfg = CellCfg<DIR, TX, TY, RPT, STAGES, CPS, SWEEP>;
   static bool configured = false;
   if (!configured) {
     CLV_CUDA(cudaFuncSetAttribute(advec_cell_tma_kernel<DIR, SWEEP, TX, TY, RPT, STAGES, CPS>,
@@ -681,8 +690,10 @@ static void launch_cell(const Grid& g, const CellMaps& M, const double* d_old, d
 // rows 1 .. ny+2: the reference stores mass_flux_y up to face y_max+2 (advec_cell_kernel_c.c:219), cells beyond ny are
 // not updated.  ncu on the three-phase kernel: top stalls `wait` and `barrier`, 23 % of the rows of a box are halo.
 constexpr int YM_R = 4, YM_G = 8, YM_W = 32, YM_H = YM_G * YM_R, YM_BW = YM_W + 4, YM_BH = YM_H + 5, YM_STAGES = 2;
-using MarchRing = TileRing<CA_NARR, YM_BW, YM_BH, YM_STAGES>;
-constexpr int YM_SMEM = MarchRing::BYTES + 128;
+template <int SWEEP>
+using MarchRing = TileRing<cell_narr(SWEEP), YM_BW, YM_BH, YM_STAGES>;
+template <int SWEEP>
+constexpr int ym_smem() { return MarchRing<SWEEP>::BYTES + 128; }
 
 template <int SWEEP>
 __global__ void __launch_bounds__(YM_W* YM_G, 2)
@@ -694,7 +705,7 @@ __global__ void __launch_bounds__(YM_W* YM_G, 2)
   constexpr int NT = YM_W * YM_G, BW = YM_BW;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = align128(smem_raw);
-  MarchRing ring;
+  MarchRing<SWEEP> ring;
   ring.init(smem);
   const int tid = threadIdx.x, lx = tid % YM_W, grp = tid / YM_W;
   const int G = gridDim.x;
@@ -746,8 +757,8 @@ __global__ void __launch_bounds__(YM_W* YM_G, 2)
     for (int i = 0; i < YM_R + 3; ++i) vd[i] = vertexd[clampi(kA - 1 + i, -1, smax) + 1];
     ring.wait(stage, (uint32_t)((it / YM_STAGES) & 1));
     const double* __restrict__ svol = ring.tile(stage, CA_VOLUME);
-    const double* __restrict__ sfx = ring.tile(stage, CA_VFX);
-    const double* __restrict__ sfy = ring.tile(stage, CA_VFY);
+    const double* __restrict__ sfy = ring.tile(stage, CA_VF);
+    const double* __restrict__ sfx = ring.tile(stage, SWEEP == 1 ? CA_VFC : CA_VOLUME);  // (read for SWEEP 1 only)
     const double* __restrict__ sd = ring.tile(stage, CA_DENSITY1);
     const double* __restrict__ se = ring.tile(stage, CA_ENERGY1);
     if (j <= nx && kA <= smax) {
@@ -816,7 +827,8 @@ static void launch_cell_ymarch(const Grid& g, const CellMaps& M, const double* d
                                double* e_new, double* mass_flux, const double* vertexd) {
   static bool configured = false;
   if (!configured) {
-    CLV_CUDA(cudaFuncSetAttribute(advec_cell_ymarch_tma_kernel<SWEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, YM_SMEM));
+    CLV_CUDA(cudaFuncSetAttribute(advec_cell_ymarch_tma_kernel<SWEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ym_smem<SWEEP>()));
     configured = true;
   }
   const int ntx = (g.nx + YM_W - 1) / YM_W, nty = (g.ny + 2 + YM_H - 1) / YM_H;  // rows 1 .. ny+2 (faces up to y_max+2)
@@ -824,7 +836,7 @@ static void launch_cell_ymarch(const Grid& g, const CellMaps& M, const double* d
   const int cap = sm_count() * 2;
   const int ctas = ntiles < cap ? ntiles : cap;
   const TileOrder ord = tile_order_split(ntx, nty, YM_W, YM_H, 2, YM_BW - 2 - YM_W, 2, YM_BH - 2 - YM_H, g.nx, g.ny);
-  launch_pdl(advec_cell_ymarch_tma_kernel<SWEEP>, dim3(ctas), dim3(YM_W * YM_G), YM_SMEM, stream(), M, d_old, d_new, e_old, e_new,
+  launch_pdl(advec_cell_ymarch_tma_kernel<SWEEP>, dim3(ctas), dim3(YM_W * YM_G), ym_smem<SWEEP>(), stream(), M, d_old, d_new, e_old, e_new,
              mass_flux, vertexd, g.nx, g.ny, g.pitch, ntiles, ord.table, next_tickets(), dep_start_for(ord), current_trace());
 }
 static bool ymarch_enabled() {
@@ -845,7 +857,7 @@ void run_advec_cell_tma(const Grid& g, int dir, int sweep, double* vertexdx, dou
   double* e_new = dev_alt(g, energy1, CELL);
   const double* vd = dir == 1 ? dev(g, vertexdx, X1D_VERT, IN) : dev(g, vertexdy, Y1D_VERT, IN);
   double* mf = dir == 1 ? dev(g, mass_flux_x, XFACE, OUT_FULL) : dev(g, mass_flux_y, YFACE, OUT_FULL);
-  const double* in[CA_NARR] = {vol, fx, fy, d_old, e_old};
+  const double* in[CA_NARR] = {vol, dir == 1 ? fx : fy, d_old, e_old, dir == 1 ? fy : fx};
   CellMaps M;
   LaunchScope ls(dir == 1 ? "advec_cell_x_tma" : "advec_cell_y_tma");
 #define CLV_CELL(DIR, TX, TY, RPT, ST, CPS)                                                                \
@@ -861,7 +873,7 @@ void run_advec_cell_tma(const Grid& g, int dir, int sweep, double* vertexdx, dou
   if (dir == 1) {
     // (a barrier-free x variant -- a warp per row segment, the fluxes of face j+1 by warp shuffle, 30-wide tiles -- was
     // bit-identical but slower: 0.187 vs 0.178 ms, profiles/r02_experiment_xrow.json)
-    CLV_CELL(1, 64, 4, 2, 2, 3);
+    CLV_CELL(1, 64, 4, 2, 2, CELLX_CPS);
   } else if (ymarch_enabled()) {
     for (int a = 0; a < CA_NARR; ++a) M.m[a] = *tensor_map_for(g, in[a], YM_BW, YM_BH);
     if (sweep == 1) launch_cell_ymarch<1>(g, M, d_old, d_new, e_old, e_new, mf, vd);
@@ -902,7 +914,8 @@ void run_advec_mom_tma(const Grid& g, int dirn, int sweep, double* vel_a, double
     else                launch_mom<DIR, DIR + 2, TX, TY, RPT, ST, CPS>(g, M, va_old, va_new, vb_old, vb_new, cd); \
   } while (0)
   // <thread grid TX x TY, rows per thread, ring stages, CTAs per SM>; measured on B200 at 3840^2:
-  //   x: <64,4,2,2,2> 0.211 ms, <64,4,1,2,4> 0.216, <64,8,1,2,2> 0.221, <64,4,2,3,2> 0.229, <64,2,4,2,2> 0.305
+  //   x: <64,4,2,2,3> 0.177 ms (fits since the flux planes moved into dead boxes; 80 registers, no spills),
+  //      <64,4,2,2,2> 0.204, <64,4,1,2,4> 0.216, <64,8,1,2,2> 0.221, <64,4,2,3,2> 0.229, <64,2,4,2,2> 0.305
   //   y: <32,8,3,2,2> 0.214 ms, <32,8,2,2,3> 0.236, <32,4,4,2,3> 0.240, <32,8,2,2,2> 0.247, <32,16,1,2,2> 0.255
   if (dirn == 1) {
     CLV_MOM(1, 64, 4, 2, 2, 3);

@@ -143,6 +143,8 @@ __device__ __forceinline__ double timestep_cell_lean(const TsCell& C, const doub
 // ---- T with TMA tile staging (tma.cuh): persistent CTAs of 32x8 threads, one cell per thread, the seven input
 // fields of a 32x8 tile arrive as 36x10 boxes with corner (j0-2, k0-1).  Same arithmetic as timestep_kernel.
 constexpr int TT_W = BX, TT_H = BY, TT_BW = TT_W + 4, TT_BH = TT_H + 2, TT_NARR = 7;
+// measured on B200 at 3840^2: (stages, CTAs/SM) = (4,2) 0.243 ms at 127 registers; three CTAs per SM need 80 registers,
+// which spills ~140 bytes: (3,3) 0.278, (2,3) 0.256 (profiles/r02_experiment_occupancy.txt)
 #ifndef TT_STAGES
 #define TT_STAGES 4
 #endif
