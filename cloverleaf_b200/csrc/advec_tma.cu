@@ -65,6 +65,7 @@ struct MomCfg {
   // the two momentum-flux planes live in the volume / density1 boxes of the stage, dead after phase A
   static_assert(NI <= BW * BH, "a plane must fit a box");
   static constexpr int SMEM = Ring::BYTES + 2 * NI * 8 + 128;
+  static_assert(fits_sm(SMEM, CPS), "advec_mom: CPS CTAs of this shape do not fit one SM");
 };
 struct MomMaps {
   CUtensorMap m[MA_NARR];
@@ -288,14 +289,21 @@ static void launch_mom(const Grid& g, const MomMaps& M, const double* va_old, do
 // boxes; nothing travels between threads, so there are no planes and no barriers between phases.  The flux through the
 // node face under a group is evaluated twice (once by the group below) instead of handed over behind a barrier.
 // Boxes: columns j0-2 .. j0+33, rows k0-2 .. k0+H+1.  MM_R = 3 keeps the six-box ring at two CTAs per SM.
-constexpr int MM_R = 3, MM_G = 8, MM_W = 32, MM_H = MM_G * MM_R, MM_BW = MM_W + 4, MM_BH = MM_H + 4, MM_STAGES = 2;
+#ifndef MM_R_
+#define MM_R_ 3
+#endif
+#ifndef MM_CPS
+#define MM_CPS 2
+#endif
+constexpr int MM_R = MM_R_, MM_G = 8, MM_W = 32, MM_H = MM_G * MM_R, MM_BW = MM_W + 4, MM_BH = MM_H + 4, MM_STAGES = 2;
 template <int MS>
 using MomMarchRing = TileRing<mom_narr(MS), MM_BW, MM_BH, MM_STAGES>;
 template <int MS>
 constexpr int mm_smem() { return MomMarchRing<MS>::BYTES + 128; }
+static_assert(fits_sm(mm_smem<1>(), MM_CPS), "advec_mom march: MM_CPS CTAs do not fit one SM");
 
 template <int MS>  // mom_sweep 2 (first sweep along y) or 4 (second sweep along y)
-__global__ void __launch_bounds__(MM_W* MM_G, 2)
+__global__ void __launch_bounds__(MM_W* MM_G, MM_CPS)
     advec_mom_ymarch_tma_kernel(const __grid_constant__ MomMaps M, const double* __restrict__ va_old, double* __restrict__ va_new,
                                 const double* __restrict__ vb_old, double* __restrict__ vb_new,
                                 const double* __restrict__ celld, int nx, int ny, int pitch, int ntiles,
@@ -442,7 +450,7 @@ static void launch_mom_ymarch(const Grid& g, const MomMaps& M, const double* va_
   }
   const int ntx = (g.nx + 1 + MM_W - 1) / MM_W, nty = (g.ny + 1 + MM_H - 1) / MM_H;
   const int ntiles = ntx * nty;
-  const int cap = sm_count() * 2;
+  const int cap = sm_count() * MM_CPS;
   const int ctas = ntiles < cap ? ntiles : cap;
   const TileOrder ord = tile_order_split(ntx, nty, MM_W, MM_H, 2, MM_BW - 2 - MM_W, 2, MM_BH - 2 - MM_H, g.nx, g.ny);
   launch_pdl(advec_mom_ymarch_tma_kernel<MS>, dim3(ctas), dim3(MM_W * MM_G), mm_smem<MS>(), stream(), M, va_old, va_new, vb_old, vb_new,
@@ -489,6 +497,7 @@ struct CellCfg {
   static_assert(NI <= BW * BH, "a plane must fit a box");
   static constexpr int NPLANES = SWEEP == 1 ? 1 : 2;
   static constexpr int SMEM = Ring::BYTES + NPLANES * NI * 8 + 128;
+  static_assert(fits_sm(SMEM, CPS), "advec_cell: CPS CTAs of this shape do not fit one SM");
 };
 struct CellMaps {
   CUtensorMap m[CA_NARR];
@@ -694,6 +703,7 @@ template <int SWEEP>
 using MarchRing = TileRing<cell_narr(SWEEP), YM_BW, YM_BH, YM_STAGES>;
 template <int SWEEP>
 constexpr int ym_smem() { return MarchRing<SWEEP>::BYTES + 128; }
+static_assert(fits_sm(ym_smem<1>(), 2), "advec_cell march: two CTAs do not fit one SM");
 
 template <int SWEEP>
 __global__ void __launch_bounds__(YM_W* YM_G, 2)

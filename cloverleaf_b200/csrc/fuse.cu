@@ -154,6 +154,7 @@ constexpr int TT_W = BX, TT_H = BY, TT_BW = TT_W + 4, TT_BH = TT_H + 2, TT_NARR 
 enum { TA_D0 = 0, TA_E0, TA_U0, TA_V0, TA_VOL, TA_XA, TA_YA };
 using TimestepRing = TileRing<TT_NARR, TT_BW, TT_BH, TT_STAGES>;
 constexpr int TT_SMEM = TimestepRing::BYTES + 128;
+static_assert(fits_sm(TT_SMEM, TT_CPS), "timestep: TT_CPS CTAs do not fit one SM");
 struct TimestepMaps {
   CUtensorMap m[TT_NARR];
 };
@@ -329,6 +330,7 @@ constexpr int PT_W = BX, PT_H = BY, PT_BW = PT_W + 2, PT_BH = PT_H + 1, PT_NARR 
 enum { PA_XAREA = 0, PA_YAREA, PA_VOLUME, PA_DENSITY0, PA_ENERGY0, PA_PRESSURE, PA_VISCOSITY, PA_XVEL0, PA_YVEL0 };
 using PredictRing = TileRing<PT_NARR, PT_BW, PT_BH, PT_STAGES>;
 constexpr int PT_SMEM = PredictRing::BYTES + 128;
+static_assert(fits_sm(PT_SMEM, PT_CPS), "pdv_predict: PT_CPS CTAs do not fit one SM");
 struct PredictMaps {
   CUtensorMap m[PT_NARR];
 };
@@ -559,6 +561,7 @@ struct CorrectCfg {
   static constexpr int NVERT = VW * (LT_H + 1);
   static constexpr int VPT = (NVERT + NT - 1) / NT;  // vertices per thread
   static constexpr int SMEM = Ring::BYTES + 2 * NVERT * 8 + 128;
+  static_assert(fits_sm(SMEM, CPS), "lagrange_correct: CPS CTAs of this shape do not fit one SM");
 };
 
 template <int W, int RPT, int STAGES, int CPS>

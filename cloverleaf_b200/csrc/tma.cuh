@@ -90,6 +90,13 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)map) : "memory");
 }
 
+// Shared memory of one SM (228 KB on sm_100) against what CPS resident CTAs take: the dynamic bytes, the few static
+// words of the tile queue, and the 1 KB the system reserves per CTA.  A kernel whose __launch_bounds__ promises CPS
+// CTAs per SM asserts this, so that a tile-shape change cannot silently halve its occupancy.
+constexpr bool fits_sm(int dyn_smem_bytes, int ctas_per_sm) {
+  return (long long)ctas_per_sm * (dyn_smem_bytes + 128 + 1024) <= 228 * 1024 && dyn_smem_bytes <= 227 * 1024;
+}
+
 // Ring of STAGES shared-memory stages, each holding NARR boxes of BW x BH doubles (each box padded to 128 B).
 template <int NARR, int BW, int BH, int STAGES>
 struct TileRing {
