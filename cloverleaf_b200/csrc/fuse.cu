@@ -539,6 +539,12 @@ __global__ void __launch_bounds__(CT_W* CT_BY)
 // the vertices / faces of the tile plus the extra row and column.  The arithmetic is that of
 // lagrange_correct_kernel, statement for statement.
 constexpr int LT_H = 8, LT_BH = LT_H + 2, LT_NARR = 9;
+#ifndef LC_W
+#define LC_W 64
+#endif
+#ifndef LC_CPS
+#define LC_CPS 2
+#endif
 #ifndef LC_FASTDIV
 #define LC_FASTDIV 1
 #endif
@@ -1107,7 +1113,7 @@ static size_t fuse_correct(const Op* q, size_t n, size_t i) {
     // <tile width, rows per thread, ring stages, CTAs per SM>; measured on B200 at 3840^2: <64,2,2,2> 0.337 ms,
     // <64,1,4,1> 0.424, <64,2,4,1> 0.452, <64,4,2,2> 0.369, <64,1,2,2> 0.403, <32,2,2,3> 0.358, <32,2,2,4> 0.430
     LaunchScope ls("lagrange_correct_tma");
-    launch_correct_tma<64, 2, 2, 2>(A, g, ac.sv[0]);
+    launch_correct_tma<LC_W, 2, 2, LC_CPS>(A, g, ac.sv[0]);
     return 3;
   }
   const dim3 grid((unsigned)((g.nx + 1 + CT_W - 1) / CT_W), (unsigned)((g.ny + 1 + CT_H - 1) / CT_H));
