@@ -481,6 +481,12 @@ static bool mom_ymarch_enabled() {
 #ifndef CELLX_TY
 #define CELLX_TY 4
 #endif
+#ifndef CELLX_RPT
+#define CELLX_RPT 2
+#endif
+#ifndef MOMX_RPT
+#define MOMX_RPT 2
+#endif
 #ifndef MOMX_TY
 #define MOMX_TY 4
 #endif
@@ -892,7 +898,7 @@ void run_advec_cell_tma(const Grid& g, int dir, int sweep, double* vertexdx, dou
   if (dir == 1) {
     // (a barrier-free x variant -- a warp per row segment, the fluxes of face j+1 by warp shuffle, 30-wide tiles -- was
     // bit-identical but slower: 0.187 vs 0.178 ms, profiles/r02_experiment_xrow.json)
-    CLV_CELL(1, 64, CELLX_TY, 2, 2, CELLX_CPS);
+    CLV_CELL(1, 64, CELLX_TY, CELLX_RPT, 2, CELLX_CPS);
   } else if (ymarch_enabled()) {
     for (int a = 0; a < CA_NARR; ++a) M.m[a] = *tensor_map_for(g, in[a], YM_BW, YM_BH);
     if (sweep == 1) launch_cell_ymarch<1>(g, M, d_old, d_new, e_old, e_new, mf, vd);
@@ -937,7 +943,7 @@ void run_advec_mom_tma(const Grid& g, int dirn, int sweep, double* vel_a, double
   //      <64,4,2,2,2> 0.204, <64,4,1,2,4> 0.216, <64,8,1,2,2> 0.221, <64,4,2,3,2> 0.229, <64,2,4,2,2> 0.305
   //   y: <32,8,3,2,2> 0.214 ms, <32,8,2,2,3> 0.236, <32,4,4,2,3> 0.240, <32,8,2,2,2> 0.247, <32,16,1,2,2> 0.255
   if (dirn == 1) {
-    CLV_MOM(1, 64, MOMX_TY, 2, 2, MOMX_CPS);
+    CLV_MOM(1, 64, MOMX_TY, MOMX_RPT, 2, MOMX_CPS);
   } else if (mom_ymarch_enabled()) {
     for (int a = 0; a < MA_NARR; ++a) M.m[a] = *tensor_map_for(g, in[a], MM_BW, MM_BH);
     if (mom_sweep == 2) launch_mom_ymarch<2>(g, M, va_old, va_new, vb_old, vb_new, cd);

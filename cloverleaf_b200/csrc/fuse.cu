@@ -140,13 +140,21 @@ __device__ __forceinline__ double timestep_cell_lean(const TsCell& C, const doub
   return calc_dt_cell_lean<SAFE>(D, P, bad, mask);
 }
 
-// ---- T with TMA tile staging (tma.cuh): persistent CTAs of 32x8 threads, one cell per thread, the seven input
-// fields of a 32x8 tile arrive as 36x10 boxes with corner (j0-2, k0-1).  Same arithmetic as timestep_kernel.
-constexpr int TT_W = BX, TT_H = BY, TT_BW = TT_W + 4, TT_BH = TT_H + 2, TT_NARR = 7;
-// measured on B200 at 3840^2: (stages, CTAs/SM) = (4,2) 0.243 ms at 127 registers; three CTAs per SM need 80 registers,
+// ---- T with TMA tile staging (tma.cuh): persistent CTAs of 32x8 threads, TT_RPT cells per thread, the seven input
+// fields of a 32 x 8*TT_RPT tile arrive as 36 x (8*TT_RPT+2) boxes with corner (j0-2, k0-1).  Same arithmetic as
+// timestep_kernel.
+// Rows per thread (rows ly, ly+BY, ...; unrolled, so that the division / square-root chains of independent cells
+// interleave -- the kernel's top stall is the fixed-latency dependency wait).  Measured on B200 at 3840^2, 2 CTAs/SM
+// (profiles/r02_experiment_timestep_rows.txt): 1 row x 4 stages 0.243 ms, 2 rows x 3 stages 0.212, 2 x 2 0.213,
+// 2 rows one after the other (unroll 1) 0.232.
+#ifndef TT_RPT
+#define TT_RPT 2
+#endif
+constexpr int TT_W = BX, TT_H = BY * TT_RPT, TT_BW = TT_W + 4, TT_BH = TT_H + 2, TT_NARR = 7;
+// With one row per thread: (stages, CTAs/SM) = (4,2) 0.243 ms at 127 registers; three CTAs per SM need 80 registers,
 // which spills ~140 bytes: (3,3) 0.278, (2,3) 0.256 (profiles/r02_experiment_occupancy.txt)
 #ifndef TT_STAGES
-#define TT_STAGES 4
+#define TT_STAGES 3
 #endif
 #ifndef TT_CPS
 #define TT_CPS 2
@@ -198,7 +206,7 @@ __global__ void __launch_bounds__(BX* BY, TT_CPS)
     }
   }
   // this iteration's tile sits in registers: it was read from the ring's table during the previous iteration (slot
-  // stage+1 is written STAGES-2 >= 2 iterations before it is due, behind at least one barrier)
+  // stage+1 is refilled STAGES-1 >= 1 iterations before it is read, i.e. behind at least one barrier)
   int t = s_tile[0];
   int2 cur = s_xy[0];
   __syncthreads();  // slot 0 has been read: the scheduler may refill it
@@ -214,10 +222,16 @@ __global__ void __launch_bounds__(BX* BY, TT_CPS)
         issue_tile(ns, s_xy[ns]);
       }
     }
-    const int j = 1 + cur.x * TT_W + lx, k = 1 + cur.y * TT_H + ly;
-    const bool active = j <= nx && k <= ny;
-    const int jc = j <= nx ? j : nx, kc = k <= ny ? k : ny;  // 1-D geometry of the threads beyond the chunk
-    const double dsx = celldx[jc + 1], dsy = celldy[kc + 1], dsx1 = celldx[jc + 2], dsy1 = celldy[kc + 2];
+    const int j = 1 + cur.x * TT_W + lx, k_top = 1 + cur.y * TT_H + ly;
+    const int jc = j <= nx ? j : nx;  // 1-D geometry of the threads beyond the chunk
+    const double dsx = celldx[jc + 1], dsx1 = celldx[jc + 2];
+    double dsy_r[TT_RPT], dsy1_r[TT_RPT];
+#pragma unroll
+    for (int r = 0; r < TT_RPT; ++r) {
+      const int kr = k_top + r * BY, kc = kr <= ny ? kr : ny;
+      dsy_r[r] = celldy[kc + 1];
+      dsy1_r[r] = celldy[kc + 2];
+    }
     ring.wait(stage, (uint32_t)((it / TT_STAGES) & 1));
     const int t_nx = s_tile[(stage + 1) % TT_STAGES];
     const int2 xy_nx = s_xy[(stage + 1) % TT_STAGES];
@@ -228,7 +242,12 @@ __global__ void __launch_bounds__(BX* BY, TT_CPS)
     const double* __restrict__ svol = ring.tile(stage, TA_VOL);
     const double* __restrict__ sxa = ring.tile(stage, TA_XA);
     const double* __restrict__ sya = ring.tile(stage, TA_YA);
-    const int b = (ly + 1) * TT_BW + lx + 2;
+#pragma unroll
+    for (int r = 0; r < TT_RPT; ++r) {
+    const int lyr = ly + r * BY, k = k_top + r * BY;
+    const bool active = j <= nx && k <= ny;
+    const double dsy = dsy_r[r], dsy1 = dsy1_r[r];
+    const int b = (lyr + 1) * TT_BW + lx + 2;
     TsCell C;
     C.rho = sd[b]; C.en = se[b];
     C.u00 = su[b]; C.u10 = su[b + 1]; C.u01 = su[b + TT_BW]; C.u11 = su[b + TT_BW + 1];
@@ -264,6 +283,7 @@ __global__ void __launch_bounds__(BX* BY, TT_CPS)
         }
       }
     }
+    }  // rows of this thread
     __syncthreads();  // the stage (read on demand above: neighbour pressures of compressing / rim cells) can be refilled
     t = t_nx;
     cur = xy_nx;
@@ -319,7 +339,10 @@ __global__ void __launch_bounds__(BX* BY)
 }
 
 // ---- P with TMA tile staging: 32x8 threads, one cell per thread, nine 34x9 boxes with corner (j0, k0) ------------
-constexpr int PT_W = BX, PT_H = BY, PT_BW = PT_W + 2, PT_BH = PT_H + 1, PT_NARR = 9;
+#ifndef PT_RPT
+#define PT_RPT 1  // tile rows per thread (rows ly, ly+BY, ...), unrolled
+#endif
+constexpr int PT_W = BX, PT_H = BY * PT_RPT, PT_BW = PT_W + 2, PT_BH = PT_H + 1, PT_NARR = 9;
 // measured on B200 at 3840^2: (stages, CTAs/SM) = (4,2) 0.202 ms, (2,4) 0.217, (3,3) 0.228
 #ifndef PT_STAGES
 #define PT_STAGES 4
@@ -370,7 +393,7 @@ __global__ void __launch_bounds__(BX* BY, PT_CPS)
     }
   }
   // this iteration's tile sits in registers: it was read from the ring's table during the previous iteration (slot
-  // stage+1 is written STAGES-2 >= 2 iterations before it is due, behind at least one barrier)
+  // stage+1 is refilled STAGES-1 >= 1 iterations before it is read, i.e. behind at least one barrier)
   int t = s_tile[0];
   int2 cur = s_xy[0];
   __syncthreads();  // slot 0 has been read: the scheduler may refill it
@@ -386,7 +409,7 @@ __global__ void __launch_bounds__(BX* BY, PT_CPS)
         issue_tile(ns, s_xy[ns]);
       }
     }
-    const int j = 1 + cur.x * PT_W + lx, k = 1 + cur.y * PT_H + ly;
+    const int j = 1 + cur.x * PT_W + lx, k_top = 1 + cur.y * PT_H + ly;
     ring.wait(stage, (uint32_t)((it / PT_STAGES) & 1));
     const int t_nx = s_tile[(stage + 1) % PT_STAGES];
     const int2 xy_nx = s_xy[(stage + 1) % PT_STAGES];
@@ -394,33 +417,42 @@ __global__ void __launch_bounds__(BX* BY, PT_CPS)
     const double* __restrict__ sya = ring.tile(stage, PA_YAREA);
     const double* __restrict__ sx = ring.tile(stage, PA_XVEL0);
     const double* __restrict__ sy = ring.tile(stage, PA_YVEL0);
-    const int b = ly * PT_BW + lx;
-    const double x00 = sx[b], x10 = sx[b + 1], x01 = sx[b + PT_BW], x11 = sx[b + PT_BW + 1];
-    const double y00 = sy[b], y10 = sy[b + 1], y01 = sy[b + PT_BW], y11 = sy[b + PT_BW + 1];
-    const double vol = ring.tile(stage, PA_VOLUME)[b], rho0 = ring.tile(stage, PA_DENSITY0)[b];
-    const double pres = ring.tile(stage, PA_PRESSURE)[b], visc = ring.tile(stage, PA_VISCOSITY)[b];
-    const double en0 = ring.tile(stage, PA_ENERGY0)[b];
-    const double xa0 = sxa[b], xa1 = sxa[b + 1], ya0 = sya[b], ya1 = sya[b + PT_BW];
+    double x00[PT_RPT], x10[PT_RPT], x01[PT_RPT], x11[PT_RPT], y00[PT_RPT], y10[PT_RPT], y01[PT_RPT], y11[PT_RPT];
+    double vol[PT_RPT], rho0[PT_RPT], pres[PT_RPT], visc[PT_RPT], en0[PT_RPT], xa0[PT_RPT], xa1[PT_RPT], ya0[PT_RPT], ya1[PT_RPT];
+#pragma unroll
+    for (int r = 0; r < PT_RPT; ++r) {
+      const int b = (ly + r * BY) * PT_BW + lx;
+      x00[r] = sx[b]; x10[r] = sx[b + 1]; x01[r] = sx[b + PT_BW]; x11[r] = sx[b + PT_BW + 1];
+      y00[r] = sy[b]; y10[r] = sy[b + 1]; y01[r] = sy[b + PT_BW]; y11[r] = sy[b + PT_BW + 1];
+      vol[r] = ring.tile(stage, PA_VOLUME)[b]; rho0[r] = ring.tile(stage, PA_DENSITY0)[b];
+      pres[r] = ring.tile(stage, PA_PRESSURE)[b]; visc[r] = ring.tile(stage, PA_VISCOSITY)[b];
+      en0[r] = ring.tile(stage, PA_ENERGY0)[b];
+      xa0[r] = sxa[b]; xa1[r] = sxa[b + 1]; ya0[r] = sya[b]; ya1[r] = sya[b + PT_BW];
+    }
     __syncthreads();  // everything this tile needs is in registers: the stage can be refilled
-    if (j <= nx && k <= ny) {
-      // PdV_kernel_c.c:63-113 (predictor), ideal_gas_kernel_c.c:48-59 on the predicted state
-      const double left = xa0 * (x00 + x01 + x00 + x01) * 0.25 * dt * 0.5;
-      const double right = xa1 * (x10 + x11 + x10 + x11) * 0.25 * dt * 0.5;
-      const double bottom = ya0 * (y00 + y10 + y00 + y10) * 0.25 * dt * 0.5;
-      const double top = ya1 * (y01 + y11 + y01 + y11) * 0.25 * dt * 0.5;
-      const double total = right - left + top - bottom;
-      const double vc = vol / (vol + total);
-      const double recip = 1.0 / vol;
-      const double de = (pres / rho0 + ddiv(visc, rho0)) * total * recip;
-      const double e1 = en0 - de;
-      const double d1 = rho0 * vc;
-      bool bad = false;
-      double p, ss;
-      ideal_gas_cell<false>(d1, e1, p, ss, bad);
-      if (bad) ideal_gas_cell<true>(d1, e1, p, ss, bad);
-      const size_t c = idx2(pitch, j, k);
-      pressure[c] = p;
-      if (WRITE_SS) soundspeed[c] = ss;
+#pragma unroll
+    for (int r = 0; r < PT_RPT; ++r) {
+      const int k = k_top + r * BY;
+      if (j <= nx && k <= ny) {
+        // PdV_kernel_c.c:63-113 (predictor), ideal_gas_kernel_c.c:48-59 on the predicted state
+        const double left = xa0[r] * (x00[r] + x01[r] + x00[r] + x01[r]) * 0.25 * dt * 0.5;
+        const double right = xa1[r] * (x10[r] + x11[r] + x10[r] + x11[r]) * 0.25 * dt * 0.5;
+        const double bottom = ya0[r] * (y00[r] + y10[r] + y00[r] + y10[r]) * 0.25 * dt * 0.5;
+        const double top = ya1[r] * (y01[r] + y11[r] + y01[r] + y11[r]) * 0.25 * dt * 0.5;
+        const double total = right - left + top - bottom;
+        const double vc = vol[r] / (vol[r] + total);
+        const double recip = 1.0 / vol[r];
+        const double de = (pres[r] / rho0[r] + ddiv(visc[r], rho0[r])) * total * recip;
+        const double e1 = en0[r] - de;
+        const double d1 = rho0[r] * vc;
+        bool bad = false;
+        double p, ss;
+        ideal_gas_cell<false>(d1, e1, p, ss, bad);
+        if (bad) ideal_gas_cell<true>(d1, e1, p, ss, bad);
+        const size_t c = idx2(pitch, j, k);
+        pressure[c] = p;
+        if (WRITE_SS) soundspeed[c] = ss;
+      }
     }
     t = t_nx;
     cur = xy_nx;
