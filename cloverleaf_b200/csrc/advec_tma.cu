@@ -295,7 +295,10 @@ static void launch_mom(const Grid& g, const MomMaps& M, const double* va_old, do
 #ifndef MM_CPS
 #define MM_CPS 2
 #endif
-constexpr int MM_R = MM_R_, MM_G = 8, MM_W = 32, MM_H = MM_G * MM_R, MM_BW = MM_W + 4, MM_BH = MM_H + 4, MM_STAGES = 2;
+#ifndef MM_G_
+#define MM_G_ 8
+#endif
+constexpr int MM_R = MM_R_, MM_G = MM_G_, MM_W = 32, MM_H = MM_G * MM_R, MM_BW = MM_W + 4, MM_BH = MM_H + 4, MM_STAGES = 2;
 template <int MS>
 using MomMarchRing = TileRing<mom_narr(MS), MM_BW, MM_BH, MM_STAGES>;
 template <int MS>
@@ -713,7 +716,13 @@ static void launch_cell(const Grid& g, const CellMaps& M, const double* d_old, d
 // through shared memory behind a barrier.  Boxes: columns j0-2 .. j0+33, rows k0-2 .. k0+H+2.  The tiling covers the
 // rows 1 .. ny+2: the reference stores mass_flux_y up to face y_max+2 (advec_cell_kernel_c.c:219), cells beyond ny are
 // not updated.  ncu on the three-phase kernel: top stalls `wait` and `barrier`, 23 % of the rows of a box are halo.
-constexpr int YM_R = 4, YM_G = 8, YM_W = 32, YM_H = YM_G * YM_R, YM_BW = YM_W + 4, YM_BH = YM_H + 5, YM_STAGES = 2;
+#ifndef YM_R_
+#define YM_R_ 4
+#endif
+#ifndef YM_G_
+#define YM_G_ 8
+#endif
+constexpr int YM_R = YM_R_, YM_G = YM_G_, YM_W = 32, YM_H = YM_G * YM_R, YM_BW = YM_W + 4, YM_BH = YM_H + 5, YM_STAGES = 2;
 template <int SWEEP>
 using MarchRing = TileRing<cell_narr(SWEEP), YM_BW, YM_BH, YM_STAGES>;
 template <int SWEEP>
