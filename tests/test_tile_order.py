@@ -35,7 +35,7 @@ def lib(tmp_path_factory):
 # (tile w, tile h, lo_x, hi_x, lo_y, hi_y, extra columns, extra rows of the tiled range) of the production launches
 # (fuse.cu, advec_tma.cu): the vertex kernels tile 1..n+1, the y march of advec_cell tiles the rows 1..ny+2
 SHAPES = {
-    "timestep": (32, 8, 2, 2, 1, 1, 0, 0), "pdv_predict": (32, 8, 0, 2, 0, 1, 0, 0), "lagrange_correct": (64, 8, 2, 2, 1, 1, 1, 1),
+    "timestep": (32, 16, 2, 2, 1, 1, 0, 0), "timestep_one_row": (32, 8, 2, 2, 1, 1, 0, 0), "pdv_predict": (32, 8, 0, 2, 0, 1, 0, 0), "lagrange_correct": (64, 8, 2, 2, 1, 1, 1, 1),
     "advec_cell_x": (60, 8, 2, 4, 0, 1, 0, 0), "advec_cell_y_three_phase": (32, 13, 2, 2, 2, 3, 0, 0),
     "advec_cell_y_march": (32, 32, 2, 2, 2, 3, 0, 2),
     "advec_mom_x": (60, 8, 2, 2, 1, 1, 1, 1), "advec_mom_y_three_phase": (32, 20, 2, 2, 2, 2, 1, 1),
