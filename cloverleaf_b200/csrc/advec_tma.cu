@@ -719,6 +719,9 @@ static void launch_cell(const Grid& g, const CellMaps& M, const double* d_old, d
 #ifndef YM_R_
 #define YM_R_ 4
 #endif
+#ifndef YM_CPS
+#define YM_CPS 2
+#endif
 #ifndef YM_G_
 #define YM_G_ 8
 #endif
@@ -727,10 +730,10 @@ template <int SWEEP>
 using MarchRing = TileRing<cell_narr(SWEEP), YM_BW, YM_BH, YM_STAGES>;
 template <int SWEEP>
 constexpr int ym_smem() { return MarchRing<SWEEP>::BYTES + 128; }
-static_assert(fits_sm(ym_smem<1>(), 2), "advec_cell march: two CTAs do not fit one SM");
+static_assert(fits_sm(ym_smem<1>(), YM_CPS), "advec_cell march: YM_CPS CTAs do not fit one SM");
 
 template <int SWEEP>
-__global__ void __launch_bounds__(YM_W* YM_G, 2)
+__global__ void __launch_bounds__(YM_W* YM_G, YM_CPS)
     advec_cell_ymarch_tma_kernel(const __grid_constant__ CellMaps M, const double* __restrict__ d_old, double* __restrict__ d_new,
                                  const double* __restrict__ e_old, double* __restrict__ e_new,
                                  double* __restrict__ mass_flux, const double* __restrict__ vertexd, int nx, int ny, int pitch,
@@ -867,7 +870,7 @@ static void launch_cell_ymarch(const Grid& g, const CellMaps& M, const double* d
   }
   const int ntx = (g.nx + YM_W - 1) / YM_W, nty = (g.ny + 2 + YM_H - 1) / YM_H;  // rows 1 .. ny+2 (faces up to y_max+2)
   const int ntiles = ntx * nty;
-  const int cap = sm_count() * 2;
+  const int cap = sm_count() * YM_CPS;
   const int ctas = ntiles < cap ? ntiles : cap;
   const TileOrder ord = tile_order_split(ntx, nty, YM_W, YM_H, 2, YM_BW - 2 - YM_W, 2, YM_BH - 2 - YM_H, g.nx, g.ny);
   launch_pdl(advec_cell_ymarch_tma_kernel<SWEEP>, dim3(ctas), dim3(YM_W * YM_G), ym_smem<SWEEP>(), stream(), M, d_old, d_new, e_old, e_new,
