@@ -338,7 +338,8 @@ __global__ void __launch_bounds__(BX* BY)
   CLV_ROWS_END
 }
 
-// ---- P with TMA tile staging: 32x8 threads, one cell per thread, nine 34x9 boxes with corner (j0, k0) ------------
+// ---- P with TMA tile staging: 32x8 threads, PT_RPT (one) cell per thread, nine 34 x (8*PT_RPT+1) boxes with corner
+// (j0, k0); two cells per thread make the kernel 4 % faster and the step 1 % slower (r02_experiment_timestep_rows.txt)
 #ifndef PT_RPT
 #define PT_RPT 1  // tile rows per thread (rows ly, ly+BY, ...), unrolled
 #endif
