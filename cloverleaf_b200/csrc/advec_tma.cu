@@ -45,10 +45,33 @@ __device__ __forceinline__ void ring_copy(const double* __restrict__ src, double
   }
 }
 
+// ---- tile shapes of the x sweeps as build macros (the defaults are the measured optimum, profiles/
+// r02_experiment_occupancy.txt, r02_experiment_timestep_rows.txt): thread rows, rows per thread, CTAs per SM.
+// advec_cell x, CTAs per SM: with the flux planes inside dead boxes four fit, but 64 registers spill (94 bytes) and
+// the launch is slower: 0.201 vs 0.178 ms (profiles/r02_experiment_occupancy.txt)
+#ifndef CELLX_CPS
+#define CELLX_CPS 3
+#endif
+#ifndef CELLX_TY
+#define CELLX_TY 4
+#endif
+#ifndef CELLX_RPT
+#define CELLX_RPT 2
+#endif
+#ifndef MOMX_RPT
+#define MOMX_RPT 2
+#endif
+#ifndef MOMX_TY
+#define MOMX_TY 4
+#endif
+#ifndef MOMX_CPS
+#define MOMX_CPS 3
+#endif
+
 enum { MA_VOLUME = 0, MA_DENSITY1, MA_MASS_FLUX, MA_VEL_A, MA_VEL_B, MA_VOL_FLUX, MA_NARR };
 
 // boxes a sweep stages: the post-volume of mom_sweep 1 / 2 needs a volume flux (:69-121), that of 3 / 4 does not --
-// the sixth box is then neither loaded nor given room (one of 8.5 passes less: these launches are DRAM-heavy)
+// the sixth box is then neither loaded nor given room (one of eight passes less)
 constexpr int mom_narr(int ms) { return ms <= 2 ? MA_NARR : MA_NARR - 1; }
 
 template <int DIR, int TX, int TY, int RPT, int STAGES, int CPS, int MS = 1>
@@ -476,26 +499,6 @@ static bool mom_ymarch_enabled() {
 // Boxes: CA_VF is the volume flux along the sweep, CA_VFC the one across it.  Only the pre-volume of the first sweep of a
 // step reads the cross flux (:77-81 / :189-193 against :94-96 / :207-209), so the second sweep neither loads that box
 // nor gives it room (one of eight passes less).
-// CTAs per SM of the x sweep: with the flux planes inside dead boxes four fit, but 64 registers spill (94 bytes) and
-// the launch is slower: 0.201 vs 0.178 ms (profiles/r02_experiment_occupancy.txt)
-#ifndef CELLX_CPS
-#define CELLX_CPS 3
-#endif
-#ifndef CELLX_TY
-#define CELLX_TY 4
-#endif
-#ifndef CELLX_RPT
-#define CELLX_RPT 2
-#endif
-#ifndef MOMX_RPT
-#define MOMX_RPT 2
-#endif
-#ifndef MOMX_TY
-#define MOMX_TY 4
-#endif
-#ifndef MOMX_CPS
-#define MOMX_CPS 3
-#endif
 enum { CA_VOLUME = 0, CA_VF, CA_DENSITY1, CA_ENERGY1, CA_VFC, CA_NARR };
 constexpr int cell_narr(int sweep) { return sweep == 1 ? CA_NARR : CA_NARR - 1; }
 
